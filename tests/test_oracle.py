@@ -1,0 +1,103 @@
+"""CPU: oracle/voicebox_oracle.py against the golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py).  fp32 vs fp32 on the same torch build: tolerance 2e-6 relative (the restatement uses
+the same ATen ops; observed difference is 0)."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import voicebox_oracle as O
+
+VB_CASES = ['voicebox_d128_l2_h4_n200', 'voicebox_d64_l2_h2_n300_sigma']
+
+
+def vb_cfg(a):
+    dim, depth, heads, batch, seq, thd = [int(v) for v in a['cfg']]
+    return dict(depth=depth, heads=heads, num_register_tokens=16, qk_norm=True, condition_on_text=False), dim, seq
+
+
+def close(a, b, tol=2e-6):
+    scale = max(float(b.abs().max()), 1e-6)
+    assert float((a - b).abs().max()) <= tol * scale + 1e-7, float((a - b).abs().max())
+
+
+@pytest.mark.parametrize('name', VB_CASES)
+def test_voicebox_loss_grads_pred(golden, name):
+    a, sd = golden(name)
+    cfg, dim, seq = vb_cfg(a)
+    sigma = float(a['sigma'])
+    sdg = {k: v.clone().requires_grad_(v.is_floating_point() and k != 'voicebox.null_cond') for k, v in sd.items()}
+    loss = O.cfm_loss(sdg, cfg, a['x1'], sigma=sigma, cond_mask=a['cond_mask'], x0=a['x0'], times=a['times'])
+    close(loss.detach(), a['loss'])
+    loss.backward()
+    for k, g in a.items():
+        if k.startswith('grad/'):
+            close(sdg['voicebox.' + k[5:]].grad, g, tol=2e-5)
+    w, flow = O.cfm_interpolate(a['x0'], a['x1'], a['times'], sigma)
+    with torch.no_grad():
+        pred = O.voicebox_forward(sd, cfg, w, times=a['times'], cond=flow, cond_mask=a['cond_mask'], prefix='voicebox.')
+    close(pred, a['pred'])
+
+
+@pytest.mark.parametrize('name', VB_CASES)
+def test_wrapper_rng_draw_order(golden, name):
+    """randn_like(x1) -> rand(B) -> uniform_(0.7,1) -> uniform_(0,1) from one generator (vp.py:1399,1403,1025,146)."""
+    a, sd = golden(name)
+    cfg, _, _ = vb_cfg(a)
+    torch.manual_seed(4242)
+    with torch.no_grad():
+        loss = O.cfm_loss(sd, cfg, a['x1'], sigma=float(a['sigma']))
+    close(loss, a['loss_wrapper_seed4242'])
+
+
+@pytest.mark.parametrize('name', VB_CASES)
+def test_sampling_midpoint_euler(golden, name):
+    a, sd = golden(name)
+    cfg, _, _ = vb_cfg(a)
+    with torch.no_grad():
+        s = O.cfm_sample(sd, cfg, cond=a['cond'], cond_mask=a['sample_cond_mask'], steps=3, method='midpoint', y0=a['y0'])
+        close(s, a['sample_midpoint_steps3'])
+        s = O.cfm_sample(sd, cfg, cond=a['cond'], cond_mask=a['sample_cond_mask'], steps=4, method='euler', y0=a['y0'])
+        close(s, a['sample_euler_steps4'])
+
+
+def test_duration_predictor_eval(golden):
+    a, sd = golden('durpred_d128_l2_h2_n100')
+    dim, depth, heads = [int(v) for v in a['cfg'][:3]]
+    with torch.no_grad():
+        d = O.duration_predictor_forward(sd, dict(depth=depth, heads=heads, qk_norm=True), cond=a['cond'],
+                                         phoneme_ids=a['phoneme_ids'], cond_mask=a['cond_mask'])
+    close(d, a['durations'])
+
+
+def test_mask_kats_bit_exact(golden):
+    a, _ = golden('kats')
+    torch.manual_seed(1234)
+    fl = torch.zeros(4).float().uniform_(0.7, 1.0)
+    assert torch.equal(fl, a['kat1234_frac'])
+    m = O.mask_from_frac_lengths(1024, fl)
+    assert torch.equal(m, a['kat1234_mask'])
+    assert hashlib.sha256(m.numpy().tobytes()).hexdigest()[:16] == 'c8da7e29c2954a7e'
+    torch.manual_seed(7)
+    assert torch.equal(O.prob_mask_like((8,), 0.3, 'cpu'), a['kat7_prob_mask'])
+    for seq in (17, 512, 1024, 2048):
+        m = O.mask_from_frac_lengths(seq, a[f'sweep{seq}_frac'], rand=a[f'sweep{seq}_rand'])
+        assert np.array_equal(np.packbits(m.numpy(), axis=-1), a[f'sweep{seq}_mask'].numpy())
+
+
+def test_rotary_and_geglu_kats(golden):
+    a, _ = golden('kats')
+    inv_freq = 1.0 / (50000 ** (torch.arange(0, 64, 2).float() / 64))
+    ang = O.rotary_angles(torch.tensor([-10000, 0, 1, 1023]), inv_freq)
+    assert torch.equal(ang, a['rotary_m10000_0_1_1023'])
+    sd = {'0.weight': torch.eye(4), '0.bias': torch.zeros(4), '3.weight': torch.eye(2), '3.bias': torch.zeros(2)}
+    assert torch.allclose(O.feed_forward(sd, '', torch.tensor([[1., 2., 3., 4.]])), a['geglu_1234'], atol=1e-6)
+
+
+def test_fully_masked_keys_give_uniform_attention():
+    """attend.py:127-128: -finfo.max fill => all-masked rows attend uniformly."""
+    torch.manual_seed(0)
+    q, k, v = torch.randn(3, 1, 2, 5, 8).unbind(0)
+    o = O.attend(q, k, v, 1.0, torch.zeros(1, 5, dtype=torch.bool))
+    assert torch.allclose(o, v.mean(-2, keepdim=True).expand_as(o), atol=1e-6)
