@@ -1,0 +1,161 @@
+/*
+ * vbx.h -- C ABI of libvbx_sm100a.so: the B200-native (sm_100a) kernels of the Voicebox conditional-flow-matching
+ * hot path (lucidrains/voicebox-pytorch @ v0.5.0, `vp.py` = voicebox_pytorch/voicebox_pytorch.py).
+ *
+ * The reference has no operator registry / FFI: its seams are Python methods.  Each entry point below replaces the
+ * chain of ATen ops named in its comment (reference file:line) and is what a `torch.autograd.Function` inside the
+ * replaced `forward` binds through ctypes (see INTEGRATION.md for the reference-side stub).
+ *
+ * Conventions
+ *   - plain pointers + int64 sizes only; every pointer is DEVICE memory owned by the caller (torch allocator);
+ *     the library never allocates, frees or retains device memory.
+ *   - `stream` is a cudaStream_t passed as void*; every launch goes on it; no device synchronisation inside.
+ *   - return 0 on success, a negative VBX_E_* for argument errors detected before launch, or a positive
+ *     cudaError_t from the launch.  vbx_strerror() maps both.
+ *   - bf16 = __nv_bfloat16 bits (uint16_t), f32 = float, masks = uint8_t (torch.bool storage, 0/1).
+ *   - "rows" are tokens; all row-major with the feature dimension contiguous unless a stride is given.
+ */
+#ifndef VBX_H_
+#define VBX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VBX_VERSION 100
+
+enum {
+  VBX_OK = 0,
+  VBX_E_NULL = -1,        /* required pointer is NULL */
+  VBX_E_SHAPE = -2,       /* size is <= 0 or violates a documented divisibility rule */
+  VBX_E_ALIGN = -3,       /* pointer or stride not aligned for vector / TMA access */
+  VBX_E_UNSUPPORTED = -4, /* valid in the reference but outside what this kernel implements */
+  VBX_E_DRIVER = -5       /* CUDA driver entry point (tensor-map encode) unavailable or failed */
+};
+
+int vbx_version(void);
+const char* vbx_strerror(int rc);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Fused residual add + (adaptive) RMSNorm                       replaces vp.py:237-247 (RMSNorm), 249-276 (AdaptiveRMSNorm)
+ *                                                               and the `+ x` residual adds at vp.py:468, 471.
+ *   x_out[b,r,:] = x_in[b,r,:] + branch[b,r,:]                 (branch may be NULL: x_out = x_in, x_out may be NULL)
+ *   h[b,r,:]     = x_out / max(||x_out||_2, 1e-12) * sqrt(D) * gamma[b or 0,:] (+ beta[b,:])        -> bf16
+ * x_in is addressed as x_in + b*x_batch_stride + (row0+r)*D  (lets the final norm skip the register tokens,
+ * vp.py:476-479); branch/x_out/h are dense [B, rows, D].  gamma/beta: f32 [B,D] when per_batch!=0 (adaptive,
+ * outputs of to_gamma/to_beta, vp.py:273) else gamma f32 [D] and beta NULL.   D % 8 == 0, D <= 2048.
+ * x_out may alias x_in when x_batch_stride == rows*D and row0 == 0 (inference, in-place residual stream).
+ * rstd (f32 [B*rows], may be NULL) receives 1/max(||x_out||,1e-12) for the backward. */
+int vbx_adarms_fwd(const float* x_in, int64_t x_batch_stride, int64_t row0, const uint16_t* branch, const float* gamma,
+                   const float* beta, int per_batch, float* x_out, uint16_t* h, float* rstd, int64_t B, int64_t rows,
+                   int64_t D, void* stream);
+
+/* Backward of the above.  Inputs: x (= x_out of the forward, same addressing as x_in), rstd, gamma, dh (bf16 [B,rows,D]),
+ * dx_res (f32 [B,rows,D] gradient arriving on the residual stream, may be NULL).
+ * Outputs: dx (f32, dense [B,rows,D]) = dx_res + J^T dh ; dbranch (bf16 copy of dx, may be NULL);
+ *          dgamma/dbeta: f32 [B,D] (per_batch) or [D], ACCUMULATED with atomics -- caller zeroes them. */
+int vbx_adarms_bwd(const float* x, int64_t x_batch_stride, int64_t row0, const float* rstd, const float* gamma, int per_batch,
+                   const uint16_t* dh, const float* dx_res, float* dx, uint16_t* dbranch, float* dgamma, float* dbeta,
+                   int64_t B, int64_t rows, int64_t D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * GEGLU                                                          replaces vp.py:337-340 (chunk, F.gelu, mul)
+ *   h: bf16 [T, 2*Fp], value = h[:, :Fp], gate = h[:, Fp:]  ->  out bf16 [T, Fp] = gelu_erf(gate) * value
+ * Fp is the feed-forward inner width zero-padded to a multiple of 8 by the caller (exact: gelu(0)*0 = 0). */
+int vbx_geglu_fwd(const uint16_t* h, uint16_t* out, int64_t T, int64_t Fp, void* stream);
+int vbx_geglu_bwd(const uint16_t* h, const uint16_t* dout, uint16_t* dh, int64_t T, int64_t Fp, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Conv positional embedding + residual + register-token pack      replaces vp.py:203-233 (+ caller's `+ x`, :826/:1080)
+ *                                                                 and the register-token pack, vp.py:422-425.
+ *   u[b,n,c]   = bias[c] + sum_j w[c,j] * (x[b,n+j-K/2,c] * m[b,n+j-K/2])       (depthwise, zero padded, K odd <= 31)
+ *   y[b,R+n,c] = gelu_erf(u) * m[b,n] + x[b,n,c]                                   -> f32 residual stream [B, R+N, C]
+ *   y[b,r,c]   = reg[r,c] for r < R                                               (reg may be NULL iff R == 0)
+ * x bf16 [B,N,C]; w f32 [C,K]; bias f32 [C]; m uint8 [B,N] or NULL; pre (bf16 [B,N,C], may be NULL) receives u for
+ * the backward.  C % 64 == 0. */
+int vbx_convpos_fwd(const uint16_t* x, const float* w, const float* bias, const uint8_t* mask, const float* reg,
+                    float* y, uint16_t* pre, int64_t B, int64_t N, int64_t C, int64_t K, int64_t R, void* stream);
+/* dy f32 [B,R+N,C] -> dx bf16 [B,N,C] (= dy + conv^T(g)), dw f32 [C,K], dbias f32 [C], dreg f32 [R,C]
+ * (dw/dbias/dreg ACCUMULATED with atomics; caller zeroes).  g = dy * gelu'(pre) * m. */
+int vbx_convpos_bwd(const uint16_t* x, const uint16_t* pre, const float* w, const uint8_t* mask, const float* dy,
+                    uint16_t* dx, float* dw, float* dbias, float* dreg, int64_t B, int64_t N, int64_t C, int64_t K,
+                    int64_t R, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * CFM noise/interpolation + conditioning mask + concat           replaces vp.py:1408-1410 (w, flow), vp.py:1003
+ *                                                                (cond = target), :1035 (cond * ~mask), :1075-1076 (cat)
+ *   emb[b,n,0:D]  = bf16( (1-(1-sigma) t_b) x0 + t_b x1 )
+ *   emb[b,n,D:2D] = bf16( (x1 - (1-sigma) x0) * !cond_mask[b,n] )
+ * x0,x1 f32 [B,N,D]; times f32 [B]; cond_mask uint8 [B,N]; emb bf16 [B,N,2D].  D % 8 == 0. */
+int vbx_cfm_embed(const float* x0, const float* x1, const float* times, const uint8_t* cond_mask, float sigma,
+                  uint16_t* emb, int64_t B, int64_t N, int64_t D, void* stream);
+/* General form used by VoiceBox.forward / sampling: emb[...,0:D] = bf16(x) (skipped if x NULL),
+ * emb[...,D:2D] = bf16(cond * !cond_mask) (skipped if cond NULL; cond_mask NULL = keep all). */
+int vbx_embed_concat(const float* x, const float* cond, const uint8_t* cond_mask, uint16_t* emb, int64_t B, int64_t N,
+                     int64_t D, void* stream);
+
+/* Masked-mean MSE against the flow target                        replaces vp.py:1099-1115
+ *   num[b] += sum_n m[b,n] * mean_d (pred - target)^2            (num f32 [B], ACCUMULATED; caller zeroes)
+ * target = tgt (f32 [B,N,D]) if tgt != NULL else x1 - (1-sigma) x0 recomputed on the fly.  pred bf16.
+ * The caller finishes loss = mean_b(num[b] / max(den[b],1e-5)) on [B] scalars. */
+int vbx_masked_mse_fwd(const uint16_t* pred, const float* tgt, const float* x0, const float* x1, float sigma,
+                       const uint8_t* loss_mask, float* num, int64_t B, int64_t N, int64_t D, void* stream);
+/* dpred[b,n,:] = coef[b] * m[b,n] * (pred - target)   with coef[b] = 2*gout / (D * max(den_b,1e-5) * B)  (f32 [B]) */
+int vbx_masked_mse_bwd(const uint16_t* pred, const float* tgt, const float* x0, const float* x1, float sigma,
+                       const uint8_t* loss_mask, const float* coef, uint16_t* dpred, int64_t B, int64_t N, int64_t D,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * One fused ODE stage combine                                     replaces torchdiffeq fixed-grid euler/midpoint
+ *                                                                 stage arithmetic at the vp.py:1295 call site.
+ *   dt = t[i1] - t[i0];  a = half ? 0.5*dt : dt;   y_out = y + a * f            (f bf16 = model prediction)
+ *   emb[b,n,0:D] = bf16(y_out)   if emb != NULL (refreshes the x-half of the next evaluation's to_embed input)
+ *   t_out[0]     = t[i0] + 0.5*dt if t_out != NULL (time of the midpoint evaluation, a device scalar)
+ * t is the DEVICE linspace grid: no host value is baked in, so a CUDA graph of one solver step can be replayed. */
+int vbx_ode_axpy(const float* y, const uint16_t* f, const float* t, int64_t i0, int64_t i1, int half, float* y_out,
+                 uint16_t* emb, float* t_out, int64_t B, int64_t N, int64_t D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * qk-RMSNorm + rotary + head split (attention prologue)          replaces vp.py:323-328 (rearrange, q_norm/k_norm,
+ *                                                                 apply_rotary_pos_emb) incl. vp.py:193-199, 280-287
+ * qkv bf16 [B, N, 3*H*64] (q | k | v blocks, each h-major d-minor, vp.py:320-321);
+ * cosv/sinv f32 [N,32] = cos/sin(pos (x) inv_freq) (half-split rotary: pairs (d, d+32));
+ * gq/gk f32 [H,64] or NULL (no qk-norm).  Writes qh, kh bf16 [B,H,N,64]:
+ *   q^ = rot( q/max(||q||,1e-12) * 8 * gq )     (norm skipped when gq NULL) */
+int vbx_qkrope_fwd(const uint16_t* qkv, const float* cosv, const float* sinv, const float* gq, const float* gk,
+                   uint16_t* qh, uint16_t* kh, int64_t B, int64_t N, int64_t H, void* stream);
+/* dqh f32 [B,H,N,64] (atomically accumulated by vbx_attn_bwd), dkh bf16 [B,H,N,64] -> writes the q and k blocks of
+ * dqkv (bf16 [B,N,3*H*64]; the v block is written by vbx_attn_bwd) and accumulates dgq, dgk f32 [H,64]. */
+int vbx_qkrope_bwd(const uint16_t* qkv, const float* cosv, const float* sinv, const float* gq, const float* gk,
+                   const float* dqh, const uint16_t* dkh, uint16_t* dqkv, float* dgq, float* dgk, int64_t B, int64_t N,
+                   int64_t H, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Attention core (tcgen05 + TMEM + TMA)                           replaces attend.py:100-137 (math path) /
+ *                                                                 attend.py:71-98 (SDPA path), head merge vp.py:332
+ *   O = softmax(scale * Q K^T, masked keys -> -FLT_MAX) V          dim_head = 64
+ * q,k bf16 [B,H,N,64]; v bf16 addressed v + b*v_bs + n*v_ns + h*64 (element strides; lets V be read in place from
+ * the qkv GEMM output); key_mask uint8 [B,N] or NULL; o bf16 [B,N,H*64]; lse f32 [B,H,N] (log2 domain, for bwd). */
+int vbx_attn_fwd(const uint16_t* q, const uint16_t* k, const uint16_t* v, int64_t v_bs, int64_t v_ns,
+                 const uint8_t* key_mask, float scale, uint16_t* o, float* lse, int64_t B, int64_t H, int64_t N,
+                 void* stream);
+/* delta f32 [B,H,N] workspace; dq f32 [B,H,N,64] ACCUMULATED (caller zeroes); dk bf16 [B,H,N,64];
+ * dv bf16 addressed like v (dv_bs/dv_ns). */
+int vbx_attn_bwd(const uint16_t* q, const uint16_t* k, const uint16_t* v, int64_t v_bs, int64_t v_ns,
+                 const uint8_t* key_mask, float scale, const uint16_t* o, const uint16_t* dout, const float* lse,
+                 float* delta, float* dq, uint16_t* dk, uint16_t* dv, int64_t dv_bs, int64_t dv_ns, int64_t B,
+                 int64_t H, int64_t N, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * tcgen05 / TMA self-test: c (f32 [128,128]) = A B^T with K = 128 through the same shared-memory / instruction
+ * descriptors the attention kernels use.  a, b: bf16 [128,128].  variant bit0: B is MN-major (b holds [K][N]),
+ * bit1: A is MN-major (a holds [K][M]), bit2: stage operands with TMA instead of thread stores. */
+int vbx_umma_selftest(const uint16_t* a, const uint16_t* b, float* c, int variant, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VBX_H_ */

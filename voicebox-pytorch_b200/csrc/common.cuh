@@ -1,0 +1,122 @@
+// Shared device helpers for libvbx_sm100a (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vbx.h"
+
+#define VBX_DEVINL __device__ __forceinline__
+
+namespace vbx {
+
+constexpr int kNumSM = 148;  // B200: 2 dies x 74 SMs
+
+struct alignas(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+VBX_DEVINL float2 bf2f(__nv_bfloat162 v) { return __bfloat1622float2(v); }
+VBX_DEVINL __nv_bfloat162 f2bf(float a, float b) { return __floats2bfloat162_rn(a, b); }
+
+// 16-byte streaming loads/stores: these tensors are touched once per kernel, keep them out of L1.
+VBX_DEVINL uint4 ldg_nc_16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+// same, without .nc: for buffers the same kernel may also write (in-place residual stream)
+VBX_DEVINL uint4 ldg_16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+VBX_DEVINL void stg_16(void* p, uint4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+VBX_DEVINL void unpack8(uint4 u, float f[8]) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = bf2f(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+VBX_DEVINL uint4 pack8(const float f[8]) {
+  uint4 u;
+  __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = f2bf(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+VBX_DEVINL void ld8f(const float* p, float f[8]) {
+  uint4 a = ldg_nc_16(p), b = ldg_nc_16(p + 4);
+  f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
+  f[4] = __uint_as_float(b.x); f[5] = __uint_as_float(b.y); f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
+}
+VBX_DEVINL void ld8f_rw(const float* p, float f[8]) {
+  uint4 a = ldg_16(p), b = ldg_16(p + 4);
+  f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
+  f[4] = __uint_as_float(b.x); f[5] = __uint_as_float(b.y); f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
+}
+VBX_DEVINL void st8f(float* p, const float f[8]) {
+  stg_16(p, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+  stg_16(p + 4, make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
+}
+
+VBX_DEVINL float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): 1 MUFU.EX2 + 1 MUFU.RCP + 7 FMA.  The exact-erf GELU
+// of the reference (nn.GELU(), F.gelu default) is reproduced to ~2e-7 absolute, far inside the bf16 output ulp, at a
+// third of erff()'s instruction count, which keeps the GEGLU / conv passes HBM-bound instead of issue-bound.
+// Returns Phi(x) = 0.5*(1+erf(x/sqrt2)) and e = exp(-x^2/2).
+VBX_DEVINL float normal_cdf(float x, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  e = exp2f(-1.4426950408889634f * z * z);
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float half_erfc = 0.5f * p * t * e;  // 0.5*erfc(z)
+  return x >= 0.f ? 1.0f - half_erfc : half_erfc;
+}
+VBX_DEVINL float gelu_f(float x) {
+  float e;
+  return x * normal_cdf(x, e);
+}
+// d/dx gelu(x) = Phi(x) + x * phi(x)
+VBX_DEVINL float gelu_grad_f(float x) {
+  float e;
+  const float c = normal_cdf(x, e);
+  return fmaf(x * 0.3989422804014327f, e, c);
+}
+
+inline int grid_for(int64_t work_items, int per_block, int max_blocks_per_sm = 8) {
+  int64_t g = (work_items + per_block - 1) / per_block;
+  int64_t cap = (int64_t)kNumSM * max_blocks_per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace vbx
+
+#define VBX_REQUIRE(cond, code) \
+  do {                          \
+    if (!(cond)) return (code); \
+  } while (0)
+#define VBX_ALIGNED16(p) ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
+#define VBX_LAUNCH_RC() ((int)cudaGetLastError())

@@ -1,0 +1,290 @@
+// HBM-bound fused passes of the Voicebox trunk: residual-add + (adaptive) RMSNorm, GEGLU.
+// One read and one write of every activation per pass, 16-byte vector accesses, fp32 math.
+#include "common.cuh"
+
+namespace vbx {
+
+// ------------------------------------------------------------------------------------------------------------------
+// residual add + (adaptive) RMSNorm, forward.   One warp per token row; lane l owns elements (c*32+l)*8..+8.
+// ------------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) adarms_fwd_kernel(const float* __restrict__ x_in, int64_t xbs, int64_t row0,
+                                                          const uint16_t* __restrict__ branch,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          int per_batch, float* x_out, uint16_t* __restrict__ h,
+                                                          float* __restrict__ rstd, int64_t B, int64_t rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float sqrt_d = sqrtf((float)D);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < B * rows; row += nwarps) {
+    const int64_t b = row / rows, r = row - b * rows;
+    const float* xi = x_in + b * xbs + (row0 + r) * D;
+    float v[C][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int e = (c * 32 + lane) * 8;
+      if (e < D) {
+        ld8f_rw(xi + e, v[c]);
+        if (branch != nullptr) {
+          float br[8];
+          unpack8(ldg_nc_16(branch + row * D + e), br);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[c][i] += br[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss = fmaf(v[c][i], v[c][i], ss);
+      }
+    }
+    if (x_out != nullptr) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int e = (c * 32 + lane) * 8;
+        if (e < D) st8f(x_out + row * D + e, v[c]);
+      }
+    }
+    ss = warp_sum(ss);
+    const float rinv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps (vp.py:247)
+    const float scale = sqrt_d * rinv;                    // ... then * sqrt(dim)
+    if (rstd != nullptr && lane == 0) rstd[row] = rinv;
+    const float* g = gamma + (per_batch ? b * D : 0);
+    const float* bt = beta ? beta + (per_batch ? b * D : 0) : nullptr;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int e = (c * 32 + lane) * 8;
+      if (e < D) {
+        float o[8];
+        const float4 g0 = *reinterpret_cast<const float4*>(g + e), g1 = *reinterpret_cast<const float4*>(g + e + 4);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        if (bt) {
+          const float4 b0 = *reinterpret_cast<const float4*>(bt + e), b1 = *reinterpret_cast<const float4*>(bt + e + 4);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = fmaf(v[c][i] * scale, gg[i], bb[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = v[c][i] * scale * gg[i];
+        }
+        stg_16(h + row * D + e, pack8(o));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// backward.  CTA = (batch b, chunk of RC rows); warps stride the chunk; dgamma/dbeta reduced warp -> smem -> global.
+//   g = dh*gamma*sqrt(D);  xh = x/||x||;  dx = (g - xh*(xh.g))/||x|| + dx_res;  dgamma += dh*xh*sqrt(D);  dbeta += dh
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kBwdRowsPerCta = 64;
+
+// dgamma/dbeta partial sums live in per-warp PRIVATE shared-memory slices (no atomics, no barriers in the row loop),
+// laid out [warp][2][c][half][lane] float4 so every access is conflict-free; this keeps the kernel near 100
+// registers (2 CTAs/SM) instead of 254 with register accumulators.
+template <int C>
+__global__ void __launch_bounds__(256, 2) adarms_bwd_kernel(const float* __restrict__ x, int64_t xbs, int64_t row0,
+                                                             const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                             int per_batch, const uint16_t* __restrict__ dh,
+                                                             const float* __restrict__ dx_res, float* __restrict__ dx,
+                                                             uint16_t* __restrict__ dbranch, float* __restrict__ dgamma,
+                                                             float* __restrict__ dbeta, int64_t rows, int D) {
+  extern __shared__ float4 red4[];  // [8 warps][2][C*2*32] float4
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kSlice = C * 2 * 32;  // float4 per (warp, which)
+  float4* my_g = red4 + (warp * 2 + 0) * kSlice;
+  float4* my_b = red4 + (warp * 2 + 1) * kSlice;
+  const int64_t b = blockIdx.y;
+  const int64_t r_begin = (int64_t)blockIdx.x * kBwdRowsPerCta;
+  const int64_t r_end = min(rows, r_begin + kBwdRowsPerCta);
+  const float sqrt_d = sqrtf((float)D);
+#pragma unroll
+  for (int j = 0; j < C * 2; ++j) my_g[j * 32 + lane] = my_b[j * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* g = gamma + (per_batch ? b * D : 0);
+
+  for (int64_t r = r_begin + warp; r < r_end; r += (blockDim.x >> 5)) {
+    const int64_t row = b * rows + r;
+    const float* xi = x + b * xbs + (row0 + r) * D;
+    const float rinv = rstd[row];
+    const float s1 = sqrt_d * rinv;  // d h / d x leading factor
+    float xv[C][8], gv[C][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int e = (c * 32 + lane) * 8;
+      if (e < D) {
+        ld8f(xi + e, xv[c]);
+        unpack8(ldg_nc_16(dh + row * D + e), gv[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int e = (c * 32 + lane) * 8;
+      if (e < D) {
+        const float4 g0 = *reinterpret_cast<const float4*>(g + e), g1 = *reinterpret_cast<const float4*>(g + e + 4);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float4 ag = my_g[(c * 2 + hf) * 32 + lane], ab = my_b[(c * 2 + hf) * 32 + lane];
+          float* pg = reinterpret_cast<float*>(&ag);
+          float* pb = reinterpret_cast<float*>(&ab);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = hf * 4 + k;
+            pb[k] += gv[c][i];                               // dbeta  += dh
+            pg[k] = fmaf(gv[c][i] * xv[c][i], s1, pg[k]);    // dgamma += dh * xhat * sqrt(D)
+            gv[c][i] *= gg[i];                               // dh * gamma
+            dot = fmaf(gv[c][i], xv[c][i], dot);
+          }
+          my_g[(c * 2 + hf) * 32 + lane] = ag;
+          my_b[(c * 2 + hf) * 32 + lane] = ab;
+        }
+      }
+    }
+    dot = warp_sum(dot);
+    const float s2 = s1 * rinv * rinv * dot;  // projection on x
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int e = (c * 32 + lane) * 8;
+      if (e < D) {
+        float o[8];
+        if (dx_res != nullptr) ld8f(dx_res + row * D + e, o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float d = fmaf(gv[c][i], s1, -xv[c][i] * s2);
+          o[i] = (dx_res != nullptr) ? o[i] + d : d;
+        }
+        st8f(dx + row * D + e, o);
+        if (dbranch != nullptr) stg_16(dbranch + row * D + e, pack8(o));
+      }
+    }
+  }
+  __syncthreads();
+  // cross-warp reduce + one global atomic per column per CTA
+  const float* redf = reinterpret_cast<const float*>(red4);
+  for (int col = threadIdx.x; col < D; col += blockDim.x) {
+    // element col = (c*32+l)*8 + hf*4 + k  ->  private slot ((c*2+hf)*32 + l)*4 + k
+    const int c = col >> 8, l = (col >> 3) & 31, hf = (col >> 2) & 1, k = col & 3;
+    const int slot = ((c * 2 + hf) * 32 + l) * 4 + k;
+    float sg = 0.f, sb = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      sg += redf[(w * 2 + 0) * kSlice * 4 + slot];
+      sb += redf[(w * 2 + 1) * kSlice * 4 + slot];
+    }
+    atomicAdd(dgamma + (per_batch ? b * D : 0) + col, sg);
+    if (dbeta != nullptr) atomicAdd(dbeta + (per_batch ? b * D : 0) + col, sb);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// GEGLU: out = gelu_erf(gate) * value, value = h[:, :Fp], gate = h[:, Fp:]
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) geglu_fwd_kernel(const uint16_t* __restrict__ h, uint16_t* __restrict__ out, int64_t T,
+                                                         int Fp) {
+  const int vec_per_row = Fp >> 3;
+  const int64_t total = T * vec_per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i / vec_per_row;
+    const int c = (int)(i - t * vec_per_row) << 3;
+    float val[8], gate[8], o[8];
+    unpack8(ldg_nc_16(h + t * 2 * Fp + c), val);
+    unpack8(ldg_nc_16(h + t * 2 * Fp + Fp + c), gate);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = gelu_f(gate[k]) * val[k];
+    stg_16(out + t * Fp + c, pack8(o));
+  }
+}
+
+__global__ void __launch_bounds__(256) geglu_bwd_kernel(const uint16_t* __restrict__ h, const uint16_t* __restrict__ dout,
+                                                         uint16_t* __restrict__ dh, int64_t T, int Fp) {
+  const int vec_per_row = Fp >> 3;
+  const int64_t total = T * vec_per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i / vec_per_row;
+    const int c = (int)(i - t * vec_per_row) << 3;
+    float val[8], gate[8], d[8], dv[8], dg[8];
+    unpack8(ldg_nc_16(h + t * 2 * Fp + c), val);
+    unpack8(ldg_nc_16(h + t * 2 * Fp + Fp + c), gate);
+    unpack8(ldg_nc_16(dout + t * Fp + c), d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float e;
+      const float cdf = normal_cdf(gate[k], e);
+      dv[k] = d[k] * gate[k] * cdf;                                                   // d value
+      dg[k] = d[k] * val[k] * fmaf(gate[k] * 0.3989422804014327f, e, cdf);            // d gate
+    }
+    stg_16(dh + t * 2 * Fp + c, pack8(dv));
+    stg_16(dh + t * 2 * Fp + Fp + c, pack8(dg));
+  }
+}
+
+}  // namespace vbx
+
+using namespace vbx;
+
+extern "C" int vbx_adarms_fwd(const float* x_in, int64_t x_batch_stride, int64_t row0, const uint16_t* branch,
+                              const float* gamma, const float* beta, int per_batch, float* x_out, uint16_t* h,
+                              float* rstd, int64_t B, int64_t rows, int64_t D, void* stream) {
+  VBX_REQUIRE(x_in && gamma && h, VBX_E_NULL);
+  VBX_REQUIRE(B > 0 && rows > 0 && D > 0 && D % 8 == 0 && x_batch_stride % 4 == 0, VBX_E_SHAPE);
+  VBX_REQUIRE(D <= 2048, VBX_E_UNSUPPORTED);
+  VBX_REQUIRE(VBX_ALIGNED16(x_in) && VBX_ALIGNED16(gamma) && VBX_ALIGNED16(h) && (!branch || VBX_ALIGNED16(branch)) &&
+                  (!beta || VBX_ALIGNED16(beta)) && (!x_out || VBX_ALIGNED16(x_out)),
+              VBX_E_ALIGN);
+  if (x_out != nullptr && x_out == x_in) VBX_REQUIRE(x_batch_stride == rows * D && row0 == 0, VBX_E_SHAPE);
+  const int grid = grid_for(B * rows, 8, 8);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int C = (int)((D + 255) / 256);
+#define LAUNCH(CC)                                                                                                          \
+  adarms_fwd_kernel<CC><<<grid, 256, 0, s>>>(x_in, x_batch_stride, row0, branch, gamma, beta, per_batch, x_out, h, rstd, B, \
+                                             rows, (int)D)
+  if (C <= 1) LAUNCH(1);
+  else if (C <= 2) LAUNCH(2);
+  else if (C <= 4) LAUNCH(4);
+  else LAUNCH(8);
+#undef LAUNCH
+  return VBX_LAUNCH_RC();
+}
+
+extern "C" int vbx_adarms_bwd(const float* x, int64_t x_batch_stride, int64_t row0, const float* rstd, const float* gamma,
+                              int per_batch,
+                              const uint16_t* dh, const float* dx_res, float* dx, uint16_t* dbranch, float* dgamma,
+                              float* dbeta, int64_t B, int64_t rows, int64_t D, void* stream) {
+  VBX_REQUIRE(x && rstd && gamma && dh && dx && dgamma, VBX_E_NULL);
+  VBX_REQUIRE(B > 0 && rows > 0 && D > 0 && D % 8 == 0 && x_batch_stride % 4 == 0 && B < 65536, VBX_E_SHAPE);
+  VBX_REQUIRE(D <= 2048, VBX_E_UNSUPPORTED);
+  VBX_REQUIRE(VBX_ALIGNED16(x) && VBX_ALIGNED16(dh) && VBX_ALIGNED16(dx) && (!dx_res || VBX_ALIGNED16(dx_res)) &&
+                  (!dbranch || VBX_ALIGNED16(dbranch)),
+              VBX_E_ALIGN);
+  dim3 grid((unsigned)((rows + kBwdRowsPerCta - 1) / kBwdRowsPerCta), (unsigned)B);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int C = (int)((D + 255) / 256);
+#define LAUNCH(CC)                                                                                                     \
+  {                                                                                                                    \
+    const size_t smem = 8 * 2 * (CC * 2 * 32) * sizeof(float4);                                                        \
+    cudaFuncSetAttribute(adarms_bwd_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+    adarms_bwd_kernel<CC><<<grid, 256, smem, s>>>(x, x_batch_stride, row0, rstd, gamma, per_batch, dh, dx_res, dx,     \
+                                                  dbranch, dgamma, dbeta, rows, (int)D);                               \
+  }
+  if (C <= 1) LAUNCH(1)
+  else if (C <= 2) LAUNCH(2)
+  else if (C <= 4) LAUNCH(4)
+  else LAUNCH(8)
+#undef LAUNCH
+  return VBX_LAUNCH_RC();
+}
+
+extern "C" int vbx_geglu_fwd(const uint16_t* h, uint16_t* out, int64_t T, int64_t Fp, void* stream) {
+  VBX_REQUIRE(h && out, VBX_E_NULL);
+  VBX_REQUIRE(T > 0 && Fp > 0 && Fp % 8 == 0, VBX_E_SHAPE);
+  VBX_REQUIRE(VBX_ALIGNED16(h) && VBX_ALIGNED16(out), VBX_E_ALIGN);
+  geglu_fwd_kernel<<<grid_for(T * (Fp / 8), 256, 8), 256, 0, (cudaStream_t)stream>>>(h, out, T, (int)Fp);
+  return VBX_LAUNCH_RC();
+}
+
+extern "C" int vbx_geglu_bwd(const uint16_t* h, const uint16_t* dout, uint16_t* dh, int64_t T, int64_t Fp, void* stream) {
+  VBX_REQUIRE(h && dout && dh, VBX_E_NULL);
+  VBX_REQUIRE(T > 0 && Fp > 0 && Fp % 8 == 0, VBX_E_SHAPE);
+  VBX_REQUIRE(VBX_ALIGNED16(h) && VBX_ALIGNED16(dout) && VBX_ALIGNED16(dh), VBX_E_ALIGN);
+  geglu_bwd_kernel<<<grid_for(T * (Fp / 8), 256, 8), 256, 0, (cudaStream_t)stream>>>(h, dout, dh, T, (int)Fp);
+  return VBX_LAUNCH_RC();
+}
