@@ -44,8 +44,8 @@ const char* vbx_strerror(int rc);
  *                                                               and the `+ x` residual adds at vp.py:468, 471.
  *   x_out[b,r,:] = x_in[b,r,:] + branch[b,r,:]                 (branch may be NULL: x_out = x_in, x_out may be NULL)
  *   h[b,r,:]     = x_out / max(||x_out||_2, 1e-12) * sqrt(D) * gamma[b or 0,:] (+ beta[b,:])        -> bf16
- * x_in is addressed as x_in + b*x_batch_stride + (row0+r)*D  (lets the final norm skip the register tokens,
- * vp.py:476-479); branch/x_out/h are dense [B, rows, D].  gamma/beta: f32 [B,D] when per_batch!=0 (adaptive,
+ * x_in and branch are addressed as base + b*x_batch_stride + (row0+r)*D  (lets the final norm skip the register
+ * tokens, vp.py:476-479); x_out/h are dense [B, rows, D].  gamma/beta: f32 [B,D] when per_batch!=0 (adaptive,
  * outputs of to_gamma/to_beta, vp.py:273) else gamma f32 [D] and beta NULL.   D % 8 == 0, D <= 2048.
  * x_out may alias x_in when x_batch_stride == rows*D and row0 == 0 (inference, in-place residual stream).
  * rstd (f32 [B*rows], may be NULL) receives 1/max(||x_out||,1e-12) for the backward. */

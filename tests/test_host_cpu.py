@@ -1,0 +1,141 @@
+"""CPU (`-m "not gpu"`): the host-side logic and the C-ABI boundary -- state_dict contract, bit-exact mask generation,
+exported symbols, loud failure without a GPU, and the flat-bucket gradient exchange on a 2-rank gloo group."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import voicebox_pytorch_b200 as vbx
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'vbx.h')).read()
+    declared = set(re.findall(r'^(?:int|const char\*)\s+(vbx_\w+)\s*\(', header, flags=re.M))
+    assert len(declared) >= 18
+    lib = ctypes.CDLL(vbx._lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/vbx.h but not exported'
+    assert declared == set(vbx._lib.EXPORTS)
+    assert vbx._lib.load().vbx_version() == 100
+    assert b'NULL' in vbx._lib.load().vbx_strerror(-1)
+
+
+@pytest.mark.parametrize('name,dim,depth,heads,thd', [('voicebox_d128_l2_h4_n200', 128, 2, 4, 128),
+                                                     ('voicebox_d64_l2_h2_n300_sigma', 64, 2, 2, 64)])
+def test_state_dict_contract_voicebox(golden, name, dim, depth, heads, thd):
+    """Parameter/buffer names and shapes identical to the reference's: checkpoints load both ways."""
+    _, sd = golden(name)
+    vb = vbx.VoiceBox(dim=dim, depth=depth, heads=heads, time_hidden_dim=thd, condition_on_text=False)
+    w = vbx.ConditionalFlowMatcherWrapper(voicebox=vb)
+    mine = w.state_dict()
+    assert set(mine) == set(sd)
+    for k in sd:
+        assert tuple(mine[k].shape) == tuple(sd[k].shape), k
+    w.load_state_dict(sd, strict=True)
+
+
+def test_state_dict_contract_duration_predictor(golden):
+    a, sd = golden('durpred_d128_l2_h2_n100')
+    dp = vbx.DurationPredictor(num_phoneme_tokens=50, dim_phoneme_emb=64, dim=128, depth=2, heads=2)
+    mine = dp.state_dict()
+    assert set(mine) == set(sd)  # the fixture excludes the third-party aligner.* keys
+    dp.load_state_dict(sd, strict=True)
+
+
+def test_text_conditioned_voicebox_keys():
+    vb = vbx.VoiceBox(dim=64, depth=2, heads=2, num_cond_tokens=10, dim_cond_emb=32, num_register_tokens=4)
+    sd = vb.state_dict()
+    assert sd['to_cond_emb.weight'].shape == (11, 32)
+    assert sd['to_embed.weight'].shape == (64, 64 * 2 + 32)
+    assert sd['transformer.register_tokens'].shape == (4, 64)
+    assert sd['transformer.layers.0.2.to_gamma.weight'].shape == (64, 256)
+
+
+def test_masks_bit_exact(golden):
+    a, _ = golden('kats')
+    torch.manual_seed(1234)
+    fl = torch.zeros(4).float().uniform_(0.7, 1.0)
+    assert torch.equal(vbx.mask_from_frac_lengths(1024, fl), a['kat1234_mask'])
+    torch.manual_seed(7)
+    assert torch.equal(vbx.prob_mask_like((8,), 0.3, 'cpu'), a['kat7_prob_mask'])
+    for seq in (17, 512, 1024, 2048):
+        frac, rand = a[f'sweep{seq}_frac'], a[f'sweep{seq}_rand']
+        lengths = (frac * seq).long()
+        start = ((seq - lengths) * rand).clamp(min=0)
+        m = vbx.mask_from_start_end_indices(seq, start, start + lengths)
+        assert np.array_equal(np.packbits(m.numpy(), axis=-1), a[f'sweep{seq}_mask'].numpy())
+
+
+def test_unsupported_options_raise_at_construction():
+    with pytest.raises(NotImplementedError):
+        vbx.Transformer(64, depth=2, use_gateloop_layers=True)
+    with pytest.raises(NotImplementedError):
+        vbx.Transformer(64, depth=2, attn_dropout=0.1)
+    with pytest.raises(NotImplementedError):
+        vbx.Transformer(64, depth=2, dim_head=32)
+    vb = vbx.VoiceBox(dim=64, depth=2, heads=2, condition_on_text=False)
+    with pytest.raises(NotImplementedError):
+        vbx.ConditionalFlowMatcherWrapper(voicebox=vb, use_torchode=True)
+    with pytest.raises(NotImplementedError):
+        vbx.ConditionalFlowMatcherWrapper(voicebox=vb, torchdiffeq_ode_method='dopri5')
+
+
+def test_no_cpu_fallback():
+    vb = vbx.VoiceBox(dim=64, depth=2, heads=2, condition_on_text=False)
+    w = vbx.ConditionalFlowMatcherWrapper(voicebox=vb)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        w(torch.randn(2, 32, 64))
+
+
+# ---- world_size-2 gloo: flat gradient bucket -------------------------------------------------------------------------
+def _worker(rank, world, port, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from voicebox_pytorch_b200.dist import FlatGradBucket
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 4), torch.nn.Linear(4, 4))
+    model[3].weight.requires_grad_(True)
+    unused = torch.nn.Linear(3, 3)  # never used by the loss (like duration_predictor inside the wrapper)
+    model.add_module('unused', unused)
+    bucket = FlatGradBucket(model, chunk_bytes=256)  # tiny chunks -> several collectives
+    bucket.broadcast_parameters(model)
+    assert len(bucket.chunks) > 1
+    g = torch.Generator().manual_seed(100 + rank)
+    xs = [torch.randn(5, 8, generator=g) for _ in range(2)]
+    # micro-step 1 under no_sync, micro-step 2 synced: gradient accumulation semantics of trainer.py:261-272
+    bucket.zero_grad()
+    with bucket.no_sync():
+        model[3](model[2](model[1](model[0](xs[0])))).pow(2).mean().backward()
+    model[3](model[2](model[1](model[0](xs[1])))).pow(2).mean().backward()
+    bucket.finish()
+    out[rank] = bucket.flat.clone()
+    # local (un-reduced) reference
+    ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 4), torch.nn.Linear(4, 4))
+    ref.load_state_dict({k: v for k, v in model.state_dict().items() if not k.startswith('unused')})
+    for x in xs:
+        ref(x).pow(2).mean().backward()
+    out[world + rank] = torch.cat([p.grad.reshape(-1) for p in reversed(list(ref.parameters()))])
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_gloo_world2():
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    n_unused = 3 * 3 + 3
+    mean_local = (out[world + 0] + out[world + 1]) / 2
+    for r in range(world):
+        flat = out[r]
+        assert torch.allclose(flat[:n_unused], torch.zeros(n_unused))       # unused params first (reverse order), zero
+        assert torch.allclose(flat[n_unused:], mean_local, atol=1e-6)         # mean over ranks of accumulated grads
+    assert torch.equal(out[0], out[1])

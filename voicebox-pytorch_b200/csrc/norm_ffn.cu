@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256) adarms_fwd_kernel(const float* __restrict
         ld8f_rw(xi + e, v[c]);
         if (branch != nullptr) {
           float br[8];
-          unpack8(ldg_nc_16(branch + row * D + e), br);
+          unpack8(ldg_nc_16(branch + b * xbs + (row0 + r) * D + e), br);
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[c][i] += br[i];
         }
