@@ -151,6 +151,12 @@ def test_convpos_fwd_bwd(vbx, B, N, C, K, R, masked):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def _ste_bf16(t):
+    """forward: round to bf16 (the tensor-core operand precision, = the reference's autocast cast before its einsum);
+    backward: identity."""
+    return t + (rbf(t) - t).detach()
+
+
 def _attn_reference(qkv, H, gq, gk, pos, inv_freq, scale, key_mask):
     B, N, _ = qkv.shape
     q, k, v = (t.reshape(B, N, H, 64).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
@@ -158,7 +164,7 @@ def _attn_reference(qkv, H, gq, gk, pos, inv_freq, scale, key_mask):
         q, k = O.multihead_rms_norm(q, gq), O.multihead_rms_norm(k, gk)
     ang = O.rotary_angles(pos, inv_freq)
     q, k = O.apply_rotary(ang, q), O.apply_rotary(ang, k)
-    o = O.attend(q, k, v, scale, key_mask)
+    o = O.attend(_ste_bf16(q), _ste_bf16(k), v, scale, key_mask)
     return o.transpose(1, 2).reshape(B, N, H * 64), q, k
 
 
@@ -167,14 +173,15 @@ def _attn_reference(qkv, H, gq, gk, pos, inv_freq, scale, key_mask):
     (2, 4, 216, 16, True, False),      # 1 full tile + 88-key tail (golden geometry)
     (1, 2, 128, 0, False, False),      # exactly one tile, no qk-norm (scale 1/8)
     (2, 2, 300, 0, True, True),        # key-padding mask (DurationPredictor path) + tail
+    (2, 2, 300, 0, False, True),       # multi-tile, no qk-norm (smooth softmax: tight check of the dQ/dK/dV GEMMs)
     (1, 16, 1040, 16, True, False),    # cfg3 geometry: 8 full tiles + 16
 ])
 def test_attention_fwd_bwd(vbx, B, H, N, R, qk_norm, masked):
     """qk-norm + rotary prologue + tcgen05 flash attention vs the fp32 oracle (vp.py:320-332, attend.py:119-137).
-    Tolerance: q^,k^ are rounded to bf16 (as the reference's autocast does before its einsum) and P to bf16 before PV;
-    with |logit| up to ~10*64 at scale 10 one bf16 ulp of q^.k^ moves a logit by ~2, so outputs are compared at 3e-2 of
-    the output max against the fp32 oracle evaluated on the SAME bf16-rounded q^,k^ (that isolates the kernel from the input
-    rounding) and gradients at 5e-2."""
+    Tolerance: q^,k^ are rounded to bf16 (as the reference's autocast does before its einsum) and P / dS to bf16 before
+    the second GEMMs.  With |logit| up to ~10*64 at scale 10 one bf16 ulp of q^.k^ moves a logit by ~2, so the fp32 oracle is
+    evaluated on the SAME bf16-rounded q^,k^ (straight-through rounding: that isolates the kernel from the operand rounding
+    the reference also performs); outputs are then compared at 3e-2 of the output max and gradients at 5e-2."""
     torch.manual_seed(4)
     dev = 'cuda'
     qkv = torch.randn(B, N, 3 * H * 64, device=dev).to(BF16)
@@ -203,11 +210,7 @@ def test_attention_fwd_bwd(vbx, B, H, N, R, qk_norm, masked):
     gqr = gq.clone().requires_grad_() if qk_norm else None
     gkr = gk.clone().requires_grad_() if qk_norm else None
     o_ref, q_ref, k_ref = _attn_reference(qkvr, H, gqr, gkr, pos, inv_freq, scale, key_mask)
-    # oracle attention on bf16-rounded q^,k^ (the tensor-core operands)
-    with torch.no_grad():
-        vv = qkv.float().chunk(3, dim=-1)[2].reshape(B, N, H, 64).transpose(1, 2)
-        o_same_inputs = O.attend(rbf(q_ref), rbf(k_ref), vv, scale, key_mask).transpose(1, 2).reshape(B, N, H * 64)
-    assert rel_err(o, o_same_inputs) < 3e-2
+    assert rel_err(o, o_ref) < 3e-2
     do = torch.randn_like(o_ref)
     o_ref.backward(rbf(do))
     o.backward(do.to(BF16))

@@ -9,12 +9,13 @@ import torch
 
 from oracle import voicebox_oracle as O
 
-VB_CASES = ['voicebox_d128_l2_h4_n200', 'voicebox_d64_l2_h2_n300_sigma']
+VB_CASES = ['voicebox_d128_l2_h4_n200', 'voicebox_d64_l2_h2_n300_sigma', 'voicebox_d128_l2_h4_n200_noqknorm']
 
 
 def vb_cfg(a):
     dim, depth, heads, batch, seq, thd = [int(v) for v in a['cfg']]
-    return dict(depth=depth, heads=heads, num_register_tokens=16, qk_norm=True, condition_on_text=False), dim, seq
+    qk = bool(int(a['qk_norm'])) if 'qk_norm' in a else True
+    return dict(depth=depth, heads=heads, num_register_tokens=16, qk_norm=qk, condition_on_text=False), dim, seq
 
 
 def close(a, b, tol=2e-6):

@@ -372,6 +372,8 @@ def transformer_forward(self, x, mask=None, adaptive_rmsnorm_cond=None):
     """Transformer.forward (vp.py:412-479): public entry, any float dtype in, same dtype out."""
     B, n, _ = x.shape
     x32 = x.float()
+    if x32 is x or x32.data_ptr() == x.data_ptr():
+        x32 = x32.clone()  # the trunk updates the residual stream in place under no_grad: never alias the caller's tensor
     if self.has_register_tokens:
         x32 = torch.cat((self.register_tokens.float()[None].expand(B, -1, -1), x32), dim=1)
         if exists(mask):
@@ -451,6 +453,7 @@ def _voicebox_body(self, emb, times, self_attn_mask):
     """emb: bf16 [B,N,2*dim_in(+dim_cond_emb)] = cat(x, [cond_emb], cond)  ->  prediction bf16 [B,N,dim_out]."""
     B, n, _ = emb.shape
     tr = self.transformer
+    times = _fix_times(times, B)                                                                  # vp.py:1012-1016
     h = ops.linear(emb, self.to_embed.weight, self.to_embed.bias)                                  # vp.py:1078
     conv = self.conv_embed.dw_conv1d[0]
     reg = tr.register_tokens if tr.has_register_tokens else None
