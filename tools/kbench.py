@@ -22,7 +22,13 @@ HBM = peaks.get('hbm_gbs', 6650.0)
 TF = peaks.get('bf16_tflops', 1590.0)
 
 
-def timeit(fn, iters=10, warm=3):
+ITERS = int(os.environ.get('KB_ITERS', 10))
+WARM = int(os.environ.get('KB_WARM', 3))
+
+
+def timeit(fn, iters=None, warm=None):
+    iters = ITERS if iters is None else iters
+    warm = WARM if warm is None else warm
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -114,11 +120,11 @@ def main():
     cosv, sinv = fr.cos().contiguous(), fr.sin().contiguous()
     gq, gk = torch.ones(H, 1, 64, device=dev), torch.ones(H, 1, 64, device=dev)
     vbx._lib.profile_start(['vbx_qkrope_fwd', 'vbx_attn_fwd', 'vbx_attn_bwd', 'vbx_qkrope_bwd'])
-    iters = 10
+    iters = ITERS
     qkv1 = qkv.clone().requires_grad_()
     gq1, gk1 = gq.clone().requires_grad_(), gk.clone().requires_grad_()
     do = torch.randn(B, Np, H * 64, device=dev).to(BF16)
-    for _ in range(iters + 3):
+    for _ in range(iters + WARM):
         o = ops.attention(qkv1, cosv, sinv, gq1, gk1, None, 10., H)
         o.backward(do)
     torch.cuda.synchronize()

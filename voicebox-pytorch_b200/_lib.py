@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libvbx_sm100a.so')
+LIB_PATH = os.environ.get('VBX_LIB') or os.path.join(_HERE, 'lib', 'libvbx_sm100a.so')  # VBX_LIB: trace build (tools/)
 
 _i64, _f32, _int, _vp = ctypes.c_int64, ctypes.c_float, ctypes.c_int, ctypes.c_void_p
 

@@ -21,6 +21,20 @@ constexpr int kBN = 128;  // keys per tile
 constexpr int kDh = 64;
 constexpr uint32_t kTileBytes = kBN * kDh * 2;  // 16 KB
 
+// ---- optional pipeline trace (built only with -DVBX_TRACE into lib/libvbx_trace.so; tools/trace_attn.py reads it) ----------
+#ifdef VBX_TRACE
+__device__ long long* g_trace = nullptr;
+#define TRACE(role, tile, point)                                                                            \
+  do {                                                                                                      \
+    if (g_trace != nullptr && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && (tile) < 16)         \
+      g_trace[((role) * 16 + (tile)) * 8 + (point)] = clock64();                                            \
+  } while (0)
+#else
+#define TRACE(role, tile, point) \
+  do {                           \
+  } while (0)
+#endif
+
 VBX_DEVINL float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -31,14 +45,24 @@ VBX_DEVINL float bf16_bits_to_float(uint16_t b) { return __uint_as_float((uint32
 // =====================================================================================================================
 // forward
 // =====================================================================================================================
+// CTA = 128 query rows of one (batch, head); 2 CTAs per SM.  10 warps:
+//   warps 0-7  softmax: row r = 32*(w%4)+lane (the TMEM lane quarter a warp may touch), column half w/4 -- two threads per
+//              row, each owning 64 of the 128 key columns of S and 32 of the 64 columns of O, so every SM sub-partition
+//              holds 4 softmax warps (latency hiding) instead of 1; the two halves agree on the running row max through
+//              a 1 KB shared-memory exchange + one named barrier per tile.
+//   warp 8     TMA producer (Q once; K double-buffered -- it is the latency-critical operand, needed the moment the softmax
+//              warps release S; V single-buffered -- it is only needed after the whole softmax of its tile)
+//   warp 9     TMEM allocator + tcgen05.mma issuer
 namespace fwd {
-constexpr uint32_t kOffQ = 0, kOffK = 16384, kOffV = 49152, kOffP = 81920, kOffBar = 114688, kOffBias = kOffBar + 128;
-constexpr uint32_t kSmemBytes = kOffBias + 2 * kBN * 2;  // 115,328 B -> two CTAs per SM
-enum { Q_FULL = 0, KV_FULL = 1, KV_EMPTY = 3, S_FULL = 5, S_FREE = 6, P_FULL = 7, O_FULL = 8, NUM_BARS = 9 };
+constexpr uint32_t kOffQ = 0, kOffK = 16384, kOffV = 49152, kOffP = 65536, kOffBar = 98304, kOffBias = kOffBar + 128,
+                   kOffMax = kOffBias + 2 * kBN * 4;
+constexpr uint32_t kSmemBytes = kOffMax + 2 * 2 * kBM * 4;  // 101,504 B -> two CTAs per SM
+enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 6, S_FULL = 7, S_FREE = 8, P_FULL = 9, O_FULL = 10, NUM_BARS = 11 };
 constexpr uint32_t kTmemCols = 256;  // S: [0,128)  O_tile: [128,192)
+constexpr int kThreads = 320;
 }  // namespace fwd
 
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(fwd::kThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
                 const __grid_constant__ CUtensorMap mv, const uint8_t* __restrict__ key_mask, float scale_log2,
                 uint16_t* __restrict__ o, float* __restrict__ lse, int N, int H) {
@@ -46,7 +70,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + NUM_BARS * 8);
-  uint16_t* s_bias = reinterpret_cast<uint16_t*>(smem + kOffBias);  // [2][128] bf16: 0 / -FLT_MAX-ish / -inf
+  float* s_bias = reinterpret_cast<float*>(smem + kOffBias);  // [2][128]: 0 / -FLT_MAX / -inf per key of the tile
+  float* s_max = reinterpret_cast<float*>(smem + kOffMax);    // [2][2][128]: per-tile partial row max of each column half
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kBM, h = blockIdx.y, b = blockIdx.z;
@@ -55,22 +80,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
     mbar_init(&bars[Q_FULL], 1);
-    mbar_init(&bars[KV_FULL], 1);
-    mbar_init(&bars[KV_FULL + 1], 1);
-    mbar_init(&bars[KV_EMPTY], 1);
-    mbar_init(&bars[KV_EMPTY + 1], 1);
+    mbar_init(&bars[K_FULL], 1);
+    mbar_init(&bars[K_FULL + 1], 1);
+    mbar_init(&bars[K_EMPTY], 1);
+    mbar_init(&bars[K_EMPTY + 1], 1);
+    mbar_init(&bars[V_FULL], 1);
+    mbar_init(&bars[V_EMPTY], 1);
     mbar_init(&bars[S_FULL], 1);
-    mbar_init(&bars[S_FREE], 128);
-    mbar_init(&bars[P_FULL], 128);
+    mbar_init(&bars[S_FREE], 256);
+    mbar_init(&bars[P_FULL], 256);
     mbar_init(&bars[O_FULL], 1);
     fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&mq);
     tma_prefetch_desc(&mk);
     tma_prefetch_desc(&mv);
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
@@ -79,143 +106,178 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ------------------------------------------------ TMA producer ------------------------------------------------
     if (lane == 0) {
       mbar_arrive_expect_tx(&bars[Q_FULL], kTileBytes);
       tma_load_4d(smem + kOffQ, &mq, &bars[Q_FULL], 0, q0, h, b);
       for (int j = 0; j < nkv; ++j) {
         const int st = j & 1;
-        mbar_wait(&bars[KV_EMPTY + st], ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&bars[KV_FULL + st], 2 * kTileBytes);
-        tma_load_4d(smem + kOffK + st * kTileBytes, &mk, &bars[KV_FULL + st], 0, j * kBN, h, b);
-        tma_load_4d(smem + kOffV + st * kTileBytes, &mv, &bars[KV_FULL + st], 0, j * kBN, h, b);
+        if (j + 2 < nkv) {  // warm L2 two tiles ahead
+          tma_prefetch_l2_4d(&mk, 0, (j + 2) * kBN, h, b);
+          tma_prefetch_l2_4d(&mv, 0, (j + 2) * kBN, h, b);
+        }
+        mbar_wait(&bars[K_EMPTY + st], ((j >> 1) & 1) ^ 1);  // S(j-2) has retired
+        mbar_arrive_expect_tx(&bars[K_FULL + st], kTileBytes);
+        tma_load_4d(smem + kOffK + st * kTileBytes, &mk, &bars[K_FULL + st], 0, j * kBN, h, b);
+        mbar_wait(&bars[V_EMPTY], (j & 1) ^ 1);  // PV(j-1) has retired: the single V buffer is free
+        mbar_arrive_expect_tx(&bars[V_FULL], kTileBytes);
+        tma_load_4d(smem + kOffV, &mv, &bars[V_FULL], 0, j * kBN, h, b);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ------------------------------------------------ MMA issuer --------------------------------------------------
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc(kBM, kBN, false, false);  // S = Q K^T      (both K-major)
       constexpr uint32_t idesc_o = make_idesc(kBM, kDh, false, true);   // O = P V        (V is MN-major: [keys][d])
-      const uint32_t aQ = smem_u32(smem + kOffQ), aP = smem_u32(smem + kOffP);
+      const uint32_t aQ = smem_u32(smem + kOffQ), aP = smem_u32(smem + kOffP), aV = smem_u32(smem + kOffV);
       mbar_wait(&bars[Q_FULL], 0);
       for (int j = 0; j < nkv; ++j) {
         const int st = j & 1;
-        const uint32_t aK = smem_u32(smem + kOffK + st * kTileBytes), aV = smem_u32(smem + kOffV + st * kTileBytes);
-        mbar_wait(&bars[KV_FULL + st], (j >> 1) & 1);
+        const uint32_t aK = smem_u32(smem + kOffK + st * kTileBytes);
+        TRACE(3, j, 0);
+        mbar_wait(&bars[K_FULL + st], (j >> 1) & 1);
+        TRACE(3, j, 1);
         mbar_wait(&bars[S_FREE], (j & 1) ^ 1);
+        TRACE(3, j, 2);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < kDh / 16; ++k) umma_bf16(tmem_base, desc_kmajor(aQ, k), desc_kmajor(aK, k), idesc_s, k > 0);
         umma_commit(&bars[S_FULL]);
+        umma_commit(&bars[K_EMPTY + st]);
+        TRACE(3, j, 3);
+        mbar_wait(&bars[V_FULL], j & 1);
+        TRACE(3, j, 4);
         mbar_wait(&bars[P_FULL], j & 1);
+        TRACE(3, j, 5);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < kBN / 16; ++k)
           umma_bf16(tmem_base + 128, desc_kmajor(aP, k), desc_mnmajor(aV, k), idesc_o, k > 0);
         umma_commit(&bars[O_FULL]);
-        umma_commit(&bars[KV_EMPTY + st]);
+        umma_commit(&bars[V_EMPTY]);
+        TRACE(3, j, 6);
       }
     }
   } else {
-    // ------------------------------------------------ softmax: one thread per query row ---------------------------
-    const int r = threadIdx.x;  // 0..127 == TMEM lane
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-    float m = -FLT_MAX, l = 0.f;
-    float acc[kDh];
+    // ------------------------------------------------ softmax: two threads per query row ---------------------------
+    const int half = warp >> 2;                 // which 64 key columns of S / which 32 columns of O
+    const int r = (warp & 3) * 32 + lane;       // query row of the tile == TMEM lane
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    float m = -FLT_MAX, l = 0.f;                // l: partial row sum over this thread's column half
+    float acc[32];
 #pragma unroll
-    for (int i = 0; i < kDh; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
 
     for (int j = 0; j < nkv; ++j) {
       const int k0 = j * kBN;
       const bool masked_tile = (key_mask != nullptr) || (k0 + kBN > N);  // CTA-uniform
-      const uint16_t* bias = s_bias + (j & 1) * kBN;
+      const float* bias = s_bias + (j & 1) * kBN + half * 64;
       if (masked_tile) {
-        const int key = k0 + r;
-        uint16_t v = 0;
-        if (key >= N) v = 0xFF80;                                             // -inf: the key does not exist
-        else if (key_mask != nullptr && !key_mask[(int64_t)b * N + key]) v = 0xFF7F;  // -3.39e38 ~ -finfo.max fill
-        s_bias[(j & 1) * kBN + r] = v;
-        named_bar_sync(1, 128);
+        if (half == 0) {
+          const int key = k0 + r;
+          float v = 0.f;
+          if (key >= N) v = -INFINITY;                                           // the key does not exist
+          else if (key_mask != nullptr && !key_mask[(int64_t)b * N + key]) v = -FLT_MAX;  // masked_fill(-finfo.max)
+          s_bias[(j & 1) * kBN + r] = v;
+        }
+        named_bar_sync(1, 256);
       }
+      if (threadIdx.x == 0) TRACE(4, j, 0);
       mbar_wait(&bars[S_FULL], j & 1);
+      if (threadIdx.x == 0) TRACE(4, j, 1);
       tc_fence_after();
-      // pass 1: running max of the scaled, masked logits (log2 domain)
-      float mx = m;
-#pragma unroll 1
-      for (int c = 0; c < kBN / 32; ++c) {
+      // pass 1: partial max over this thread's 64 columns (scaled, masked logits; log2 domain)
+      float mx = -FLT_MAX;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         float s[32];
-        tmem_ld32(t_lane + c * 32, s);
+        tmem_ld32(t_lane + half * 64 + c * 32, s);
         if (masked_tile) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaf(s[i], scale_log2, bf16_bits_to_float(bias[c * 32 + i])));
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaf(s[i], scale_log2, bias[c * 32 + i]));
         } else {
+          float m4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, s[i] * scale_log2);
+          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], s[i]);
+          mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale_log2);  // scale > 0
         }
       }
+      s_max[((j & 1) * 2 + half) * kBM + r] = mx;
+      if (threadIdx.x == 0) TRACE(4, j, 2);
+      named_bar_sync(2, 256);
+      if (threadIdx.x == 0) TRACE(4, j, 3);
+      mx = fmaxf(fmaxf(mx, s_max[((j & 1) * 2 + (half ^ 1)) * kBM + r]), m);
       const float alpha = ex2(m - mx);
       m = mx;
-      // pass 2: p = 2^(t - m), row sum, P -> shared memory (bf16, K-major SW128, two 64-key sub-tiles)
+      // pass 2: p = 2^(t - m), partial row sum, P -> shared memory (bf16, K-major SW128; sub-tile == column half)
       float rowsum = 0.f;
       const float neg_m = -m;
-#pragma unroll 1
-      for (int c = 0; c < kBN / 32; ++c) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         float s[32];
-        tmem_ld32(t_lane + c * 32, s);
-        if (c == kBN / 32 - 1) {  // S is in registers: the MMA warp may overwrite it
+        tmem_ld32(t_lane + half * 64 + c * 32, s);
+        if (c == 1) {  // this thread's part of S is in registers: release it to the MMA warp
           tc_fence_before();
           mbar_arrive(&bars[S_FREE]);
         }
         if (masked_tile) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) s[i] = ex2(fmaf(s[i], scale_log2, bf16_bits_to_float(bias[c * 32 + i])) + neg_m);
+          for (int i = 0; i < 32; ++i) s[i] = ex2(fmaf(s[i], scale_log2, bias[c * 32 + i]) + neg_m);
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) s[i] = ex2(fmaf(s[i], scale_log2, neg_m));
         }
+        float r4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) rowsum += s[i];
+        for (int i = 0; i < 32; ++i) r4[i & 3] += s[i];
+        rowsum += (r4[0] + r4[1]) + (r4[2] + r4[3]);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int c16 = c * 4 + q;
-          uint8_t* dst = smem + kOffP + (c16 >> 3) * kSubTileBytes + r * 128 + (((c16 & 7) ^ (r & 7)) << 4);
+          const int cc = c * 4 + q;  // 16-byte chunk inside this half's 64-key sub-tile
+          uint8_t* dst = smem + kOffP + half * kSubTileBytes + r * 128 + ((cc ^ (r & 7)) << 4);
           *reinterpret_cast<uint4*>(dst) = pack8(&s[q * 8]);
         }
       }
       l = fmaf(l, alpha, rowsum);
+      if (threadIdx.x == 0) TRACE(4, j, 4);
       fence_proxy_async();
       mbar_arrive(&bars[P_FULL]);
-      // O_acc = O_acc * alpha + P V
+      if (threadIdx.x == 0) TRACE(4, j, 5);
+      // O_acc = O_acc * alpha + (P V)[:, this thread's 32 columns]
       mbar_wait(&bars[O_FULL], j & 1);
+      if (threadIdx.x == 0) TRACE(4, j, 6);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < kDh / 32; ++c) {
+      {
         float v[32];
-        tmem_ld32(t_lane + 128 + c * 32, v);
+        tmem_ld32(t_lane + 128 + half * 32, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[c * 32 + i] = fmaf(acc[c * 32 + i], alpha, v[i]);
+        for (int i = 0; i < 32; ++i) acc[i] = fmaf(acc[i], alpha, v[i]);
       }
       tc_fence_before();
     }
-    // epilogue: normalise, merge heads ('b h n d -> b n (h d)'), log-sum-exp for the backward
+    // epilogue: total row sum (both halves), normalise, merge heads ('b h n d -> b n (h d)'), log-sum-exp for the backward
+    named_bar_sync(2, 256);                       // everyone is done reading s_max of the last tiles
+    s_max[half * kBM + r] = l;
+    named_bar_sync(2, 256);
+    l += s_max[(half ^ 1) * kBM + r];
     const int q = q0 + r;
     if (q < N) {
       const float inv_l = 1.0f / l;
-      uint16_t* dst = o + (((int64_t)b * N + q) * H + h) * kDh;
+      uint16_t* dst = o + (((int64_t)b * N + q) * H + h) * kDh + half * 32;
 #pragma unroll
-      for (int c = 0; c < kDh / 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         float t[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) t[i] = acc[c * 8 + i] * inv_l;
         stg_16(dst + c * 8, pack8(t));
       }
-      if (lse != nullptr) lse[((int64_t)b * H + h) * N + q] = m + log2f(l);
+      if (lse != nullptr && half == 0) lse[((int64_t)b * H + h) * N + q] = m + log2f(l);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 9) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // =====================================================================================================================
@@ -246,30 +308,33 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const uint16_t* __restr
     if (__all_sync(0xffffffffu, vid + stride >= nvec)) break;
   }
 }
-
 namespace bwd {
-constexpr uint32_t kOffK = 0, kOffV = 16384, kOffQ = 32768, kOffdO = 65536, kOffPT = 98304, kOffdST = 131072,
-                   kOffBar = 163840, kOffLse = kOffBar + 128, kOffDelta = kOffLse + 2 * kBM * 4;
-constexpr uint32_t kSmemBytes = kOffDelta + 2 * kBM * 4;  // 166,016 B: one CTA per SM
-enum { KV_FULL = 0, QD_FULL = 1, QD_EMPTY = 3, ST_FULL = 5, ST_FREE = 6, DS_FULL = 7, DQ_FULL = 8, NUM_BARS = 9 };
+constexpr int kStages = 3;  // Q/dO ring: the load of tile i+2 is issued as soon as the GEMMs of tile i-1 retire
+constexpr uint32_t kOffK = 0, kOffV = 16384, kOffQ = 32768, kOffdO = kOffQ + kStages * 16384, kOffPT = kOffdO + kStages * 16384,
+                   kOffdST = kOffPT + 32768, kOffdQ = kOffdST + 32768, kOffBar = kOffdQ + 32768, kOffLse = kOffBar + 128,
+                   kOffDelta = kOffLse + 2 * kBM * 4;
+constexpr uint32_t kSmemBytes = kOffDelta + 2 * kBM * 4;  // 231,552 B of the 232,448 B a CTA may use: one CTA per SM
+enum { KV_FULL = 0, QD_FULL = 1, QD_EMPTY = 4, ST_FULL = 7, ST_FREE = 8, DS_FULL = 9, DQ_FULL = 10, NUM_BARS = 11 };
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColST = 0, kColDPT = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
+constexpr int kThreads = 320;
 }  // namespace bwd
-
-VBX_DEVINL void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 // One CTA per (key tile, head, batch); loops over the query tiles.  Everything is computed TRANSPOSED (keys on the
 // TMEM lanes) so that P^T and dS^T come out K-major for the dV / dK GEMMs, which accumulate in TMEM across the loop:
 //   S^T = K Q^T, dP^T = V dO^T  ->  P^T = 2^(c S^T - lse), dS^T = P^T (dP^T - delta)
-//   dV += P^T dO,  dK += dS^T Q,  dQ_i = dS K  (fp32 red.global.add into dq; scaled by `scale`)
-__global__ void __launch_bounds__(192, 1)
+//   dV += P^T dO,  dK += dS^T Q,  dQ_i = dS K  (fp32, scaled by `scale`, staged in shared memory and added into dq by
+//   ONE TMA reduce-add per 128x32 block -- per-lane red.global atomics cost ~8000 clk per tile, 6x the five GEMMs)
+// 10 warps: 0-7 compute (key row 32*(w%4)+lane, query-column half w/4: two threads per row -> 2 warps per SM
+// sub-partition), 8 TMA producer, 9 MMA issuer.  Software pipeline: the S^T/dP^T GEMMs of tile i+1 are issued BEFORE the
+// dV/dK/dQ GEMMs of tile i, and the compute warps keep P^T/dS^T of tile i+1 in registers until those GEMMs have finished
+// reading the shared-memory operand tiles -- so tensor pipe and exp/FMA pipes overlap instead of alternating.
+__global__ void __launch_bounds__(bwd::kThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
                 const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mdo,
-                const uint8_t* __restrict__ key_mask, float scale, float scale_log2, const float* __restrict__ lse,
-                const float* __restrict__ delta, float* __restrict__ dq, uint16_t* __restrict__ dk, uint16_t* __restrict__ dv,
-                int64_t dv_bs, int64_t dv_ns, int N, int H) {
+                const __grid_constant__ CUtensorMap mdq, const uint8_t* __restrict__ key_mask, float scale, float scale_log2,
+                const float* __restrict__ lse, const float* __restrict__ delta, uint16_t* __restrict__ dk,
+                uint16_t* __restrict__ dv, int64_t dv_bs, int64_t dv_ns, int N, int H) {
   using namespace bwd;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
@@ -285,17 +350,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
     mbar_init(&bars[KV_FULL], 1);
-    mbar_init(&bars[QD_FULL], 1);
-    mbar_init(&bars[QD_FULL + 1], 1);
-    mbar_init(&bars[QD_EMPTY], 1);
-    mbar_init(&bars[QD_EMPTY + 1], 1);
+    for (int s_ = 0; s_ < kStages; ++s_) {
+      mbar_init(&bars[QD_FULL + s_], 1);
+      mbar_init(&bars[QD_EMPTY + s_], 1);
+    }
     mbar_init(&bars[ST_FULL], 1);
-    mbar_init(&bars[ST_FREE], 128);
-    mbar_init(&bars[DS_FULL], 128);
+    mbar_init(&bars[ST_FREE], 256);
+    mbar_init(&bars[DS_FULL], 256);
     mbar_init(&bars[DQ_FULL], 1);
     fence_barrier_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
@@ -304,41 +369,58 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_arrive_expect_tx(&bars[KV_FULL], 2 * kTileBytes);
       tma_load_4d(smem + kOffK, &mk, &bars[KV_FULL], 0, k0, h, b);
       tma_load_4d(smem + kOffV, &mv, &bars[KV_FULL], 0, k0, h, b);
       for (int i = 0; i < nq; ++i) {
-        const int st = i & 1;
-        mbar_wait(&bars[QD_EMPTY + st], ((i >> 1) & 1) ^ 1);
+        const int st = i % kStages;
+        if (i + kStages < nq) {  // warm L2 for the tile after the ring
+          tma_prefetch_l2_4d(&mq, 0, (i + kStages) * kBM, h, b);
+          tma_prefetch_l2_4d(&mdo, 0, (i + kStages) * kBM, h, b);
+        }
+        mbar_wait(&bars[QD_EMPTY + st], ((i / kStages) & 1) ^ 1);
+        TRACE(2, i, 0);
         mbar_arrive_expect_tx(&bars[QD_FULL + st], 2 * kTileBytes);
         tma_load_4d(smem + kOffQ + st * kTileBytes, &mq, &bars[QD_FULL + st], 0, i * kBM, h, b);
         tma_load_4d(smem + kOffdO + st * kTileBytes, &mdo, &bars[QD_FULL + st], 0, i * kBM, h, b);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       constexpr uint32_t idesc_kk = make_idesc(128, 128, false, false);
       constexpr uint32_t idesc_kmn = make_idesc(128, kDh, false, true);
       constexpr uint32_t idesc_mnmn = make_idesc(128, kDh, true, true);
       const uint32_t aK = smem_u32(smem + kOffK), aV = smem_u32(smem + kOffV), aPT = smem_u32(smem + kOffPT),
                      aDST = smem_u32(smem + kOffdST);
-      mbar_wait(&bars[KV_FULL], 0);
-      for (int i = 0; i < nq; ++i) {
-        const int st = i & 1;
+      auto issue_s = [&](int i) {  // S^T = K Q_i^T, dP^T = V dO_i^T
+        const int st = i % kStages;
         const uint32_t aQ = smem_u32(smem + kOffQ + st * kTileBytes), aDO = smem_u32(smem + kOffdO + st * kTileBytes);
-        mbar_wait(&bars[QD_FULL + st], (i >> 1) & 1);
-        mbar_wait(&bars[ST_FREE], (i & 1) ^ 1);
+        TRACE(0, i, 0);
+        mbar_wait(&bars[QD_FULL + st], (i / kStages) & 1);
+        TRACE(0, i, 1);
+        mbar_wait(&bars[ST_FREE], (i & 1) ^ 1);  // the compute warps hold tile i-1's S^T/dP^T in registers
+        TRACE(0, i, 2);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < kDh / 16; ++k)  // S^T = K Q^T
+        for (int k = 0; k < kDh / 16; ++k)
           umma_bf16(tmem_base + kColST, desc_kmajor(aK, k), desc_kmajor(aQ, k), idesc_kk, k > 0);
 #pragma unroll
-        for (int k = 0; k < kDh / 16; ++k)  // dP^T = V dO^T
+        for (int k = 0; k < kDh / 16; ++k)
           umma_bf16(tmem_base + kColDPT, desc_kmajor(aV, k), desc_kmajor(aDO, k), idesc_kk, k > 0);
         umma_commit(&bars[ST_FULL]);
+        TRACE(0, i, 3);
+      };
+      mbar_wait(&bars[KV_FULL], 0);
+      issue_s(0);
+      for (int i = 0; i < nq; ++i) {
+        const int st = i % kStages;
+        const uint32_t aQ = smem_u32(smem + kOffQ + st * kTileBytes), aDO = smem_u32(smem + kOffdO + st * kTileBytes);
+        if (i + 1 < nq) issue_s(i + 1);  // runs on the tensor pipe while the compute warps finish tile i
+        TRACE(0, i, 4);
         mbar_wait(&bars[DS_FULL], i & 1);
+        TRACE(0, i, 5);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < kBM / 16; ++k)  // dV += P^T dO
@@ -351,94 +433,123 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
           umma_bf16(tmem_base + kColDQ, desc_mnmajor(aDST, k), desc_mnmajor(aK, k), idesc_mnmn, k > 0);
         umma_commit(&bars[DQ_FULL]);
         umma_commit(&bars[QD_EMPTY + st]);
+        TRACE(0, i, 6);
       }
     }
   } else {
-    const int r = threadIdx.x;  // key row of this tile == TMEM lane
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int half = warp >> 2;              // which 64 query columns of S^T / dP^T, which 32 columns of dQ / dV / dK
+    const int r = (warp & 3) * 32 + lane;    // TMEM lane: key row (S^T, dP^T, dV, dK) or query row (dQ)
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const int key = k0 + r;
     float bias = 0.f;
     if (key >= N) bias = -INFINITY;
     else if (key_mask != nullptr && !key_mask[(int64_t)b * N + key]) bias = -FLT_MAX;
 
+    // dQ_i: TMEM -> registers -> shared ([128 rows][32 fp32] SWIZZLE_128B block per half) -> TMA reduce-add into dq
+    auto flush_dq = [&](int i) {
+      mbar_wait(&bars[DQ_FULL], i & 1);  // all GEMMs of tile i have retired: dQ_i is complete, P^T/dS^T smem is free
+      tc_fence_after();
+      if (threadIdx.x == 0) tma_wait_group_read0();  // the previous reduce has finished READING the staging buffer
+      named_bar_sync(2, 256);
+      float v[32];
+      tmem_ld32(t_lane + kColDQ + half * 32, v);
+#pragma unroll
+      for (int qd = 0; qd < 8; ++qd) {
+        float4 o4 = make_float4(v[qd * 4] * scale, v[qd * 4 + 1] * scale, v[qd * 4 + 2] * scale, v[qd * 4 + 3] * scale);
+        *reinterpret_cast<float4*>(smem + kOffdQ + half * kTileBytes + r * 128 + ((qd ^ (r & 7)) << 4)) = o4;
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      named_bar_sync(3, 256);
+      if (threadIdx.x == 0) {
+        tma_reduce_add_4d(&mdq, smem + kOffdQ, 0, i * kBM, h, b);  // rows beyond N are clipped by the tensor map
+        tma_reduce_add_4d(&mdq, smem + kOffdQ + kTileBytes, 32, i * kBM, h, b);
+        tma_commit_group();
+      }
+    };
+
     for (int i = 0; i < nq; ++i) {
       const int st = i & 1, q0 = i * kBM;
-      {
+      if (half == 0) {
         const int q = q0 + r;
         s_lse[st * kBM + r] = (q < N) ? lse[bh * N + q] : INFINITY;  // +inf -> p = 0 for padded queries
         s_delta[st * kBM + r] = (q < N) ? delta[bh * N + q] : 0.f;
-        named_bar_sync(1, 128);
       }
+      if (threadIdx.x == 0) TRACE(1, i, 0);
+      named_bar_sync(1, 256);
+      if (threadIdx.x == 0) TRACE(1, i, 1);
       mbar_wait(&bars[ST_FULL], i & 1);
+      if (threadIdx.x == 0) TRACE(1, i, 2);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < kBM / 32; ++c) {
+      uint32_t pk[2][16], dsk[2][16];  // P^T / dS^T of this thread's 64 columns, packed bf16x2, held across the flush
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         float s[32], dp[32];
-        tmem_ld32(t_lane + kColST + c * 32, s);
-        tmem_ld32(t_lane + kColDPT + c * 32, dp);
-        if (c == kBM / 32 - 1) {
+        tmem_ld32(t_lane + kColST + half * 64 + c * 32, s);
+        tmem_ld32(t_lane + kColDPT + half * 64 + c * 32, dp);
+        if (c == 1) {
           tc_fence_before();
           mbar_arrive(&bars[ST_FREE]);
         }
+        const float* lrow = s_lse + st * kBM + half * 64 + c * 32;
+        const float* drow = s_delta + st * kBM + half * 64 + c * 32;
 #pragma unroll
-        for (int x = 0; x < 32; ++x) {
-          const float p = ex2(fmaf(s[x], scale_log2, bias) - s_lse[st * kBM + c * 32 + x]);
-          s[x] = p;
-          dp[x] = p * (dp[x] - s_delta[st * kBM + c * 32 + x]);
+        for (int x = 0; x < 32; x += 2) {
+          const float p0 = ex2(fmaf(s[x], scale_log2, bias) - lrow[x]);
+          const float p1 = ex2(fmaf(s[x + 1], scale_log2, bias) - lrow[x + 1]);
+          const float d0 = p0 * (dp[x] - drow[x]);
+          const float d1 = p1 * (dp[x + 1] - drow[x + 1]);
+          __nv_bfloat162 pp = f2bf(p0, p1), dd = f2bf(d0, d1);
+          pk[c][x >> 1] = *reinterpret_cast<uint32_t*>(&pp);
+          dsk[c][x >> 1] = *reinterpret_cast<uint32_t*>(&dd);
         }
+      }
+      if (threadIdx.x == 0) TRACE(1, i, 3);
+      if (i > 0) flush_dq(i - 1);  // also the point after which the P^T / dS^T shared tiles may be overwritten
+      if (threadIdx.x == 0) TRACE(1, i, 4);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
-          const int c16 = c * 4 + qd;
-          const uint32_t off = (c16 >> 3) * kSubTileBytes + r * 128 + (((c16 & 7) ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(smem + kOffPT + off) = pack8(&s[qd * 8]);
-          *reinterpret_cast<uint4*>(smem + kOffdST + off) = pack8(&dp[qd * 8]);
+          const int cc = c * 4 + qd;  // 16-byte chunk inside this half's 64-query sub-tile
+          const uint32_t off = half * kSubTileBytes + r * 128 + ((cc ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(smem + kOffPT + off) =
+              make_uint4(pk[c][qd * 4], pk[c][qd * 4 + 1], pk[c][qd * 4 + 2], pk[c][qd * 4 + 3]);
+          *reinterpret_cast<uint4*>(smem + kOffdST + off) =
+              make_uint4(dsk[c][qd * 4], dsk[c][qd * 4 + 1], dsk[c][qd * 4 + 2], dsk[c][qd * 4 + 3]);
         }
       }
       fence_proxy_async();
+      if (threadIdx.x == 0) TRACE(1, i, 5);
       mbar_arrive(&bars[DS_FULL]);
-      // dQ tile: TMEM lane = query row
-      mbar_wait(&bars[DQ_FULL], i & 1);
-      tc_fence_after();
-      const int q = q0 + r;
-#pragma unroll
-      for (int c = 0; c < kDh / 32; ++c) {
-        float v[32];
-        tmem_ld32(t_lane + kColDQ + c * 32, v);
-        if (q < N) {
-          float* dst = dq + (bh * N + q) * kDh + c * 32;
-#pragma unroll
-          for (int x = 0; x < 32; x += 4) red_add_v4(dst + x, v[x] * scale, v[x + 1] * scale, v[x + 2] * scale, v[x + 3] * scale);
-        }
-      }
-      tc_fence_before();
+      if (threadIdx.x == 0) TRACE(1, i, 6);
     }
-    // all MMAs are complete (DQ_FULL of the last tile): write dV, dK for this key row.  The TMEM loads are
+    flush_dq(nq - 1);
+    if (threadIdx.x == 0) tma_wait_group0();
+    // all GEMMs have retired: write this thread's 32 columns of dV and dK for its key row.  The TMEM loads are
     // .sync.aligned (whole warp, converged); only the global stores are predicated on the key being real.
     {
       const bool live = key < N;
-      uint16_t* dvp = dv + (int64_t)b * dv_bs + (int64_t)(live ? key : 0) * dv_ns + h * kDh;
-      uint16_t* dkp = dk + (bh * N + (live ? key : 0)) * kDh;
+      uint16_t* dvp = dv + (int64_t)b * dv_bs + (int64_t)(live ? key : 0) * dv_ns + h * kDh + half * 32;
+      uint16_t* dkp = dk + (bh * N + (live ? key : 0)) * kDh + half * 32;
+      float v[32];
+      tmem_ld32(t_lane + kColDV + half * 32, v);
+      if (live) {
 #pragma unroll
-      for (int c = 0; c < kDh / 32; ++c) {
-        float v[32];
-        tmem_ld32(t_lane + kColDV + c * 32, v);
-        if (live) {
+        for (int x = 0; x < 32; x += 8) stg_16(dvp + x, pack8(&v[x]));
+      }
+      tmem_ld32(t_lane + kColDK + half * 32, v);
 #pragma unroll
-          for (int x = 0; x < 32; x += 8) stg_16(dvp + c * 32 + x, pack8(&v[x]));
-        }
-        tmem_ld32(t_lane + kColDK + c * 32, v);
+      for (int x = 0; x < 32; ++x) v[x] *= scale;
+      if (live) {
 #pragma unroll
-        for (int x = 0; x < 32; ++x) v[x] *= scale;
-        if (live) {
-#pragma unroll
-          for (int x = 0; x < 32; x += 8) stg_16(dkp + c * 32 + x, pack8(&v[x]));
-        }
+        for (int x = 0; x < 32; x += 8) stg_16(dkp + x, pack8(&v[x]));
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 9) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // =====================================================================================================================
@@ -529,17 +640,19 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// esize = 2 (bf16, box 64 wide) or 4 (fp32, box 32 wide): either way one box row is 128 bytes = one swizzle row
 static int make_tmap(CUtensorMap* out, const void* base, int64_t inner, int64_t N, int64_t H, int64_t B, int64_t n_stride,
-                     int64_t h_stride, int64_t b_stride, int box_rows) {
+                     int64_t h_stride, int64_t b_stride, int box_rows, int esize = 2) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return VBX_E_DRIVER;
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || (n_stride * 2) % 16 || (h_stride * 2) % 16 || (b_stride * 2) % 16)
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (n_stride * esize) % 16 || (h_stride * esize) % 16 || (b_stride * esize) % 16)
     return VBX_E_ALIGN;
   cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)N, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)n_stride * 2, (cuuint64_t)h_stride * 2, (cuuint64_t)b_stride * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+  cuuint64_t strides[3] = {(cuuint64_t)n_stride * esize, (cuuint64_t)h_stride * esize, (cuuint64_t)b_stride * esize};
+  cuuint32_t box[4] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult rc = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult rc = fn(out, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                   const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return rc == CUDA_SUCCESS ? VBX_OK : VBX_E_DRIVER;
@@ -572,7 +685,7 @@ extern "C" int vbx_attn_fwd(const uint16_t* q, const uint16_t* k, const uint16_t
     cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd::kSmemBytes);
   });
   dim3 grid((unsigned)((N + kBM - 1) / kBM), (unsigned)H, (unsigned)B);
-  attn_fwd_kernel<<<grid, 192, fwd::kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, key_mask, scale * kLog2e, o, lse, (int)N,
+  attn_fwd_kernel<<<grid, fwd::kThreads, fwd::kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, key_mask, scale * kLog2e, o, lse, (int)N,
                                                                        (int)H);
   return VBX_LAUNCH_RC();
 }
@@ -586,12 +699,13 @@ extern "C" int vbx_attn_bwd(const uint16_t* q, const uint16_t* k, const uint16_t
   VBX_REQUIRE(VBX_ALIGNED16(o) && VBX_ALIGNED16(dout) && VBX_ALIGNED16(dq) && VBX_ALIGNED16(dk) && VBX_ALIGNED16(dv) &&
                   (dv_bs % 8 == 0) && (dv_ns % 8 == 0),
               VBX_E_ALIGN);
-  CUtensorMap mq, mk, mv, mdo;
+  CUtensorMap mq, mk, mv, mdo, mdq;
   int rc;
   if ((rc = make_tmap_bf16_4d(&mq, q, N, H, B, kDh, N * kDh, H * N * kDh, kBM)) != VBX_OK) return rc;
   if ((rc = make_tmap_bf16_4d(&mk, k, N, H, B, kDh, N * kDh, H * N * kDh, kBN)) != VBX_OK) return rc;
   if ((rc = make_tmap_bf16_4d(&mv, v, N, H, B, v_ns, kDh, v_bs, kBN)) != VBX_OK) return rc;
   if ((rc = make_tmap_bf16_4d(&mdo, dout, N, H, B, H * kDh, kDh, N * H * kDh, kBM)) != VBX_OK) return rc;
+  if ((rc = make_tmap(&mdq, dq, kDh, N, H, B, kDh, N * kDh, H * N * kDh, kBM, 4)) != VBX_OK) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   attn_delta_kernel<<<grid_for(B * N * H, 32, 8), 256, 0, s>>>(o, dout, delta, B, N, (int)H);
   static std::once_flag once;
@@ -599,10 +713,16 @@ extern "C" int vbx_attn_bwd(const uint16_t* q, const uint16_t* k, const uint16_t
     cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd::kSmemBytes);
   });
   dim3 grid((unsigned)((N + kBN - 1) / kBN), (unsigned)H, (unsigned)B);
-  attn_bwd_kernel<<<grid, 192, bwd::kSmemBytes, s>>>(mq, mk, mv, mdo, key_mask, scale, scale * kLog2e, lse, delta, dq, dk, dv,
+  attn_bwd_kernel<<<grid, bwd::kThreads, bwd::kSmemBytes, s>>>(mq, mk, mv, mdo, mdq, key_mask, scale, scale * kLog2e, lse, delta, dk, dv,
                                                      dv_bs, dv_ns, (int)N, (int)H);
   return VBX_LAUNCH_RC();
 }
+
+#ifdef VBX_TRACE
+extern "C" int vbx_debug_set_trace(void* dev_ptr) {
+  return (int)cudaMemcpyToSymbol(vbx::g_trace, &dev_ptr, sizeof(void*));
+}
+#endif
 
 extern "C" int vbx_umma_selftest(const uint16_t* a, const uint16_t* b, float* c, int variant, void* stream) {
   VBX_REQUIRE(a && b && c, VBX_E_NULL);

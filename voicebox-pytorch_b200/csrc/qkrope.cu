@@ -14,6 +14,10 @@ struct VecId {
   int64_t tok;
   int which, h;
 };
+VBX_DEVINL void ld8_cached(const float* p, float f[8]) {  // small tables: let them live in L1
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
 VBX_DEVINL VecId decode(int64_t vid, int H) {
   VecId v;
   const int pair = (int)(vid % (2 * H));
@@ -45,17 +49,20 @@ __global__ void __launch_bounds__(256) qkrope_fwd_kernel(const uint16_t* __restr
       ss += __shfl_xor_sync(0xffffffffu, ss, 2);
       ss += __shfl_xor_sync(0xffffffffu, ss, 4);
       const float sc = 8.0f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize * sqrt(64)
+      float gl[8];
+      ld8_cached(gam + id.h * kDh + sub * 8, gl);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = v[i] * sc * gam[id.h * kDh + sub * 8 + i];
+      for (int i = 0; i < 8; ++i) v[i] = v[i] * sc * gl[i];
     }
-    float o[8];
+    float o[8], cs[8], sn[8];
     const int fi = (sub & 3) * 8;  // frequency index base (d mod 32)
+    ld8_cached(cosv + n * 32 + fi, cs);
+    ld8_cached(sinv + n * 32 + fi, sn);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float partner = __shfl_xor_sync(0xffffffffu, v[i], 4);
-      const float c = cosv[n * 32 + fi + i], s = sinv[n * 32 + fi + i];
       const float rot = (sub < 4) ? -partner : partner;  // rotate_half([a,b]) = [-b, a]
-      o[i] = fmaf(v[i], c, rot * s);
+      o[i] = fmaf(v[i], cs[i], rot * sn[i]);
     }
     if (active) {
       uint16_t* dst = (id.which ? kh : qh) + ((b * H + id.h) * N + n) * kDh + sub * 8;
@@ -97,13 +104,14 @@ __global__ void __launch_bounds__(256) qkrope_bwd_kernel(const uint16_t* __restr
     const int64_t goff = id.tok * (3 * H * kDh) + id.which * (H * kDh) + id.h * kDh + sub * 8;
     unpack8(ldg_nc_16(qkv + goff), x);
     // undo the rotation: dz[d] = dy[d] cos + (d<32 ? dy[d+32] : -dy[d-32]) sin
-    float dz[8];
+    float dz[8], cs[8], sn[8];
     const int fi = (sub & 3) * 8;
+    ld8_cached(cosv + n * 32 + fi, cs);
+    ld8_cached(sinv + n * 32 + fi, sn);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float partner = __shfl_xor_sync(0xffffffffu, dy[i], 4);
-      const float c = cosv[n * 32 + fi + i], s = sinv[n * 32 + fi + i];
-      dz[i] = fmaf(dy[i], c, ((sub < 4) ? partner : -partner) * s);
+      dz[i] = fmaf(dy[i], cs[i], ((sub < 4) ? partner : -partner) * sn[i]);
     }
     float o[8];
     if (gam != nullptr) {
