@@ -445,12 +445,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
     if (key >= N) bias = -INFINITY;
     else if (key_mask != nullptr && !key_mask[(int64_t)b * N + key]) bias = -FLT_MAX;
 
-    // dQ_i: TMEM -> registers -> shared ([128 rows][32 fp32] SWIZZLE_128B block per half) -> TMA reduce-add into dq
+    // dQ_i: TMEM -> registers -> shared -> TMA reduce-add into dq, with NO block-wide synchronisation: warp w owns rows
+    // [32(w%4), +32) of the [128 rows][32 fp32] SWIZZLE_128B block of its column half -- a contiguous, 1024-byte aligned
+    // 4 KB slice -- and issues its own 32x32 reduce (bulk groups are per thread: lane 0 waits for its previous one).
     auto flush_dq = [&](int i) {
       mbar_wait(&bars[DQ_FULL], i & 1);  // all GEMMs of tile i have retired: dQ_i is complete, P^T/dS^T smem is free
       tc_fence_after();
-      if (threadIdx.x == 0) tma_wait_group_read0();  // the previous reduce has finished READING the staging buffer
-      named_bar_sync(2, 256);
+      if (lane == 0) tma_wait_group_read0();  // this warp's previous reduce has finished READING its slice
+      __syncwarp();
       float v[32];
       tmem_ld32(t_lane + kColDQ + half * 32, v);
 #pragma unroll
@@ -460,20 +462,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
       }
       tc_fence_before();
       fence_proxy_async();
-      named_bar_sync(3, 256);
-      if (threadIdx.x == 0) {
-        tma_reduce_add_4d(&mdq, smem + kOffdQ, 0, i * kBM, h, b);  // rows beyond N are clipped by the tensor map
-        tma_reduce_add_4d(&mdq, smem + kOffdQ + kTileBytes, 32, i * kBM, h, b);
+      __syncwarp();
+      if (lane == 0) {  // rows beyond N are clipped by the tensor map
+        tma_reduce_add_4d(&mdq, smem + kOffdQ + half * kTileBytes + (warp & 3) * 4096, half * 32, i * kBM + (warp & 3) * 32, h, b);
         tma_commit_group();
       }
     };
 
+    float nlse = INFINITY, ndelta = 0.f;  // lse / delta of this thread's query for the NEXT tile (register prefetch)
+    if (half == 0 && r < N) {
+      nlse = lse[bh * N + r];
+      ndelta = delta[bh * N + r];
+    }
     for (int i = 0; i < nq; ++i) {
       const int st = i & 1, q0 = i * kBM;
       if (half == 0) {
-        const int q = q0 + r;
-        s_lse[st * kBM + r] = (q < N) ? lse[bh * N + q] : INFINITY;  // +inf -> p = 0 for padded queries
-        s_delta[st * kBM + r] = (q < N) ? delta[bh * N + q] : 0.f;
+        s_lse[st * kBM + r] = nlse;  // +inf -> p = 0 for padded queries
+        s_delta[st * kBM + r] = ndelta;
+        const int qn = q0 + kBM + r;  // issue the next tile's loads now: their latency hides behind this tile's math
+        nlse = INFINITY;
+        ndelta = 0.f;
+        if (i + 1 < nq && qn < N) {
+          nlse = lse[bh * N + qn];
+          ndelta = delta[bh * N + qn];
+        }
       }
       if (threadIdx.x == 0) TRACE(1, i, 0);
       named_bar_sync(1, 256);
@@ -525,7 +537,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
       if (threadIdx.x == 0) TRACE(1, i, 6);
     }
     flush_dq(nq - 1);
-    if (threadIdx.x == 0) tma_wait_group0();
+    if (lane == 0) tma_wait_group0();
     // all GEMMs have retired: write this thread's 32 columns of dV and dK for its key row.  The TMEM loads are
     // .sync.aligned (whole warp, converged); only the global stores are predicated on the key being real.
     {
@@ -705,7 +717,7 @@ extern "C" int vbx_attn_bwd(const uint16_t* q, const uint16_t* k, const uint16_t
   if ((rc = make_tmap_bf16_4d(&mk, k, N, H, B, kDh, N * kDh, H * N * kDh, kBN)) != VBX_OK) return rc;
   if ((rc = make_tmap_bf16_4d(&mv, v, N, H, B, v_ns, kDh, v_bs, kBN)) != VBX_OK) return rc;
   if ((rc = make_tmap_bf16_4d(&mdo, dout, N, H, B, H * kDh, kDh, N * H * kDh, kBM)) != VBX_OK) return rc;
-  if ((rc = make_tmap(&mdq, dq, kDh, N, H, B, kDh, N * kDh, H * N * kDh, kBM, 4)) != VBX_OK) return rc;
+  if ((rc = make_tmap(&mdq, dq, kDh, N, H, B, kDh, N * kDh, H * N * kDh, 32, 4)) != VBX_OK) return rc;  // 32x32 fp32 boxes
   cudaStream_t s = (cudaStream_t)stream;
   attn_delta_kernel<<<grid_for(B * N * H, 32, 8), 256, 0, s>>>(o, dout, delta, B, N, (int)H);
   static std::once_flag once;

@@ -8,15 +8,17 @@ namespace vbx {
 // residual add + (adaptive) RMSNorm, forward.   One warp per token row; lane l owns elements (c*32+l)*8..+8.
 // ------------------------------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(256) adarms_fwd_kernel(const float* __restrict__ x_in, int64_t xbs, int64_t row0,
+__global__ void __launch_bounds__(256, (C <= 4) ? 4 : 2) adarms_fwd_kernel(const float* __restrict__ x_in, int64_t xbs, int64_t row0,
                                                           const uint16_t* __restrict__ branch,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           int per_batch, float* x_out, uint16_t* __restrict__ h,
                                                           float* __restrict__ rstd, int64_t B, int64_t rows, int D) {
   const int lane = threadIdx.x & 31;
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const float sqrt_d = sqrtf((float)D);
-  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < B * rows; row += nwarps) {
+  // one row per warp, one block per 8 rows: the hardware block scheduler balances the tail (a grid-stride loop with ~7
+  // rows per warp costs up to 1/7 in imbalance)
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row < B * rows) {
     const int64_t b = row / rows, r = row - b * rows;
     const float* xi = x_in + b * xbs + (row0 + r) * D;
     float v[C][8];
@@ -75,7 +77,7 @@ __global__ void __launch_bounds__(256) adarms_fwd_kernel(const float* __restrict
 // backward.  CTA = (batch b, chunk of RC rows); warps stride the chunk; dgamma/dbeta reduced warp -> smem -> global.
 //   g = dh*gamma*sqrt(D);  xh = x/||x||;  dx = (g - xh*(xh.g))/||x|| + dx_res;  dgamma += dh*xh*sqrt(D);  dbeta += dh
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kBwdRowsPerCta = 64;
+// rows per CTA are chosen on the host so that the CTA count is just under a whole number of waves (2 CTAs per SM)
 
 // dgamma/dbeta partial sums live in per-warp PRIVATE shared-memory slices (no atomics, no barriers in the row loop),
 // laid out [warp][2][c][half][lane] float4 so every access is conflict-free; this keeps the kernel near 100
@@ -86,15 +88,15 @@ __global__ void __launch_bounds__(256, 2) adarms_bwd_kernel(const float* __restr
                                                              int per_batch, const uint16_t* __restrict__ dh,
                                                              const float* __restrict__ dx_res, float* __restrict__ dx,
                                                              uint16_t* __restrict__ dbranch, float* __restrict__ dgamma,
-                                                             float* __restrict__ dbeta, int64_t rows, int D) {
+                                                             float* __restrict__ dbeta, int64_t rows, int D, int rows_per_cta) {
   extern __shared__ float4 red4[];  // [8 warps][2][C*2*32] float4
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int kSlice = C * 2 * 32;  // float4 per (warp, which)
   float4* my_g = red4 + (warp * 2 + 0) * kSlice;
   float4* my_b = red4 + (warp * 2 + 1) * kSlice;
   const int64_t b = blockIdx.y;
-  const int64_t r_begin = (int64_t)blockIdx.x * kBwdRowsPerCta;
-  const int64_t r_end = min(rows, r_begin + kBwdRowsPerCta);
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r_end = min(rows, r_begin + rows_per_cta);
   const float sqrt_d = sqrtf((float)D);
 #pragma unroll
   for (int j = 0; j < C * 2; ++j) my_g[j * 32 + lane] = my_b[j * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -231,7 +233,9 @@ extern "C" int vbx_adarms_fwd(const float* x_in, int64_t x_batch_stride, int64_t
                   (!beta || VBX_ALIGNED16(beta)) && (!x_out || VBX_ALIGNED16(x_out)),
               VBX_E_ALIGN);
   if (x_out != nullptr && x_out == x_in) VBX_REQUIRE(x_batch_stride == rows * D && row0 == 0, VBX_E_SHAPE);
-  const int grid = grid_for(B * rows, 8, 8);
+  const int64_t nblk = (B * rows + 7) / 8;
+  VBX_REQUIRE(nblk < (1ll << 31), VBX_E_SHAPE);
+  const int grid = (int)nblk;
   cudaStream_t s = (cudaStream_t)stream;
   const int C = (int)((D + 255) / 256);
 #define LAUNCH(CC)                                                                                                          \
@@ -255,7 +259,16 @@ extern "C" int vbx_adarms_bwd(const float* x, int64_t x_batch_stride, int64_t ro
   VBX_REQUIRE(VBX_ALIGNED16(x) && VBX_ALIGNED16(dh) && VBX_ALIGNED16(dx) && (!dx_res || VBX_ALIGNED16(dx_res)) &&
                   (!dbranch || VBX_ALIGNED16(dbranch)),
               VBX_E_ALIGN);
-  dim3 grid((unsigned)((rows + kBwdRowsPerCta - 1) / kBwdRowsPerCta), (unsigned)B);
+  // pick rows/CTA in [32,128] minimising ceil(waves) * rows  (time ~ number of waves x rows per CTA)
+  int best_rc = 64;
+  double best_cost = 1e30;
+  for (int rc = 32; rc <= 128; ++rc) {
+    const int64_t ctas = B * ((rows + rc - 1) / rc);
+    const int64_t waves = (ctas + 2 * kNumSM - 1) / (2 * kNumSM);
+    const double cost = (double)waves * rc;
+    if (cost < best_cost - 1e-9) best_cost = cost, best_rc = rc;
+  }
+  dim3 grid((unsigned)((rows + best_rc - 1) / best_rc), (unsigned)B);
   cudaStream_t s = (cudaStream_t)stream;
   const int C = (int)((D + 255) / 256);
 #define LAUNCH(CC)                                                                                                     \
@@ -263,7 +276,7 @@ extern "C" int vbx_adarms_bwd(const float* x, int64_t x_batch_stride, int64_t ro
     const size_t smem = 8 * 2 * (CC * 2 * 32) * sizeof(float4);                                                        \
     cudaFuncSetAttribute(adarms_bwd_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
     adarms_bwd_kernel<CC><<<grid, 256, smem, s>>>(x, x_batch_stride, row0, rstd, gamma, per_batch, dh, dx_res, dx,     \
-                                                  dbranch, dgamma, dbeta, rows, (int)D);                               \
+                                                  dbranch, dgamma, dbeta, rows, (int)D, best_rc);                      \
   }
   if (C <= 1) LAUNCH(1)
   else if (C <= 2) LAUNCH(2)
