@@ -152,7 +152,8 @@ int vbx_attn_bwd(const uint16_t* q, const uint16_t* k, const uint16_t* v, int64_
 /* ---------------------------------------------------------------------------------------------------------------
  * tcgen05 / TMA self-test: c (f32 [128,128]) = A B^T with K = 128 through the same shared-memory / instruction
  * descriptors the attention kernels use.  a, b: bf16 [128,128].  variant bit0: B is MN-major (b holds [K][N]),
- * bit1: A is MN-major (a holds [K][M]), bit2: stage operands with TMA instead of thread stores. */
+ * bit1: A is MN-major (a holds [K][M]), bit2: stage operands with TMA instead of thread stores, bit3: A operand placed in
+ * TMEM with tcgen05.st and consumed by a TS-mode MMA (not combinable with bit1). */
 int vbx_umma_selftest(const uint16_t* a, const uint16_t* b, float* c, int variant, void* stream);
 
 #ifdef __cplusplus

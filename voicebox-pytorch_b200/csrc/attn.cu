@@ -50,15 +50,18 @@ VBX_DEVINL float bf16_bits_to_float(uint16_t b) { return __uint_as_float((uint32
 //              row, each owning 64 of the 128 key columns of S and 32 of the 64 columns of O, so every SM sub-partition
 //              holds 4 softmax warps (latency hiding) instead of 1; the two halves agree on the running row max through
 //              a 1 KB shared-memory exchange + one named barrier per tile.
-//   warp 8     TMA producer (Q once; K double-buffered -- it is the latency-critical operand, needed the moment the softmax
-//              warps release S; V single-buffered -- it is only needed after the whole softmax of its tile)
+//   warp 8     TMA producer (Q once; K and V double-buffered, L2 prefetch two tiles ahead)
 //   warp 9     TMEM allocator + tcgen05.mma issuer
+// P never touches shared memory: the softmax threads write it (bf16, two keys per 32-bit column) straight into TMEM with
+// tcgen05.st and O = P V runs as a TS-mode MMA (A from TMEM, only V read from shared memory).  With SS-mode MMAs the SM's
+// 128 B/clk of shared-memory bandwidth -- not the tensor pipe -- was the limiter (8 KB of operands per 64-clk MMA).
 namespace fwd {
-constexpr uint32_t kOffQ = 0, kOffK = 16384, kOffV = 49152, kOffP = 65536, kOffBar = 98304, kOffBias = kOffBar + 128,
+constexpr uint32_t kOffQ = 0, kOffK = 16384, kOffV = 49152, kOffBar = 81920, kOffBias = kOffBar + 128,
                    kOffMax = kOffBias + 2 * kBN * 4;
-constexpr uint32_t kSmemBytes = kOffMax + 2 * 2 * kBM * 4;  // 101,504 B -> two CTAs per SM
-enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 6, S_FULL = 7, S_FREE = 8, P_FULL = 9, O_FULL = 10, NUM_BARS = 11 };
-constexpr uint32_t kTmemCols = 256;  // S: [0,128)  O_tile: [128,192)
+constexpr uint32_t kSmemBytes = kOffMax + 2 * 2 * kBM * 4;  // 85,120 B -> two CTAs per SM
+enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, S_FREE = 10, P_FULL = 11, O_FULL = 12, NUM_BARS = 13 };
+constexpr uint32_t kTmemCols = 256;  // S: [0,128)  O_tile: [128,192)  P (bf16 pairs): [192,256)
+constexpr uint32_t kColO = 128, kColP = 192;
 constexpr int kThreads = 320;
 }  // namespace fwd
 
@@ -85,7 +88,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
     mbar_init(&bars[K_EMPTY], 1);
     mbar_init(&bars[K_EMPTY + 1], 1);
     mbar_init(&bars[V_FULL], 1);
+    mbar_init(&bars[V_FULL + 1], 1);
     mbar_init(&bars[V_EMPTY], 1);
+    mbar_init(&bars[V_EMPTY + 1], 1);
     mbar_init(&bars[S_FULL], 1);
     mbar_init(&bars[S_FREE], 256);
     mbar_init(&bars[P_FULL], 256);
@@ -120,9 +125,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         mbar_wait(&bars[K_EMPTY + st], ((j >> 1) & 1) ^ 1);  // S(j-2) has retired
         mbar_arrive_expect_tx(&bars[K_FULL + st], kTileBytes);
         tma_load_4d(smem + kOffK + st * kTileBytes, &mk, &bars[K_FULL + st], 0, j * kBN, h, b);
-        mbar_wait(&bars[V_EMPTY], (j & 1) ^ 1);  // PV(j-1) has retired: the single V buffer is free
-        mbar_arrive_expect_tx(&bars[V_FULL], kTileBytes);
-        tma_load_4d(smem + kOffV, &mv, &bars[V_FULL], 0, j * kBN, h, b);
+        mbar_wait(&bars[V_EMPTY + st], ((j >> 1) & 1) ^ 1);  // PV(j-2) has retired
+        mbar_arrive_expect_tx(&bars[V_FULL + st], kTileBytes);
+        tma_load_4d(smem + kOffV + st * kTileBytes, &mv, &bars[V_FULL + st], 0, j * kBN, h, b);
       }
     }
   } else if (warp == 9) {
@@ -130,11 +135,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc(kBM, kBN, false, false);  // S = Q K^T      (both K-major)
       constexpr uint32_t idesc_o = make_idesc(kBM, kDh, false, true);   // O = P V        (V is MN-major: [keys][d])
-      const uint32_t aQ = smem_u32(smem + kOffQ), aP = smem_u32(smem + kOffP), aV = smem_u32(smem + kOffV);
+      const uint32_t aQ = smem_u32(smem + kOffQ);
       mbar_wait(&bars[Q_FULL], 0);
       for (int j = 0; j < nkv; ++j) {
         const int st = j & 1;
-        const uint32_t aK = smem_u32(smem + kOffK + st * kTileBytes);
+        const uint32_t aK = smem_u32(smem + kOffK + st * kTileBytes), aV = smem_u32(smem + kOffV + st * kTileBytes);
         TRACE(3, j, 0);
         mbar_wait(&bars[K_FULL + st], (j >> 1) & 1);
         TRACE(3, j, 1);
@@ -146,16 +151,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         umma_commit(&bars[S_FULL]);
         umma_commit(&bars[K_EMPTY + st]);
         TRACE(3, j, 3);
-        mbar_wait(&bars[V_FULL], j & 1);
+        mbar_wait(&bars[V_FULL + st], (j >> 1) & 1);
         TRACE(3, j, 4);
         mbar_wait(&bars[P_FULL], j & 1);
         TRACE(3, j, 5);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < kBN / 16; ++k)
-          umma_bf16(tmem_base + 128, desc_kmajor(aP, k), desc_mnmajor(aV, k), idesc_o, k > 0);
+        for (int k = 0; k < kBN / 16; ++k)  // A = P from TMEM: 8 columns (16 keys) per K-step
+          umma_bf16_ts(tmem_base + kColO, tmem_base + kColP + k * 8, desc_mnmajor(aV, k), idesc_o, k > 0);
         umma_commit(&bars[O_FULL]);
-        umma_commit(&bars[V_EMPTY]);
+        umma_commit(&bars[V_EMPTY + st]);
         TRACE(3, j, 6);
       }
     }
@@ -210,7 +215,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
       mx = fmaxf(fmaxf(mx, s_max[((j & 1) * 2 + (half ^ 1)) * kBM + r]), m);
       const float alpha = ex2(m - mx);
       m = mx;
-      // pass 2: p = 2^(t - m), partial row sum, P -> shared memory (bf16, K-major SW128; sub-tile == column half)
+      // pass 2: p = 2^(t - m), partial row sum, P -> TMEM (bf16 pairs: column kColP + key/2 of this row's lane)
       float rowsum = 0.f;
       const float neg_m = -m;
 #pragma unroll
@@ -232,16 +237,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 32; ++i) r4[i & 3] += s[i];
         rowsum += (r4[0] + r4[1]) + (r4[2] + r4[3]);
+        uint32_t pk[16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int cc = c * 4 + q;  // 16-byte chunk inside this half's 64-key sub-tile
-          uint8_t* dst = smem + kOffP + half * kSubTileBytes + r * 128 + ((cc ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(dst) = pack8(&s[q * 8]);
+        for (int x = 0; x < 16; ++x) {
+          __nv_bfloat162 t2 = f2bf(s[2 * x], s[2 * x + 1]);
+          pk[x] = *reinterpret_cast<uint32_t*>(&t2);
         }
+        tmem_st16(t_lane + kColP + half * 32 + c * 16, pk);
       }
       l = fmaf(l, alpha, rowsum);
       if (threadIdx.x == 0) TRACE(4, j, 4);
-      fence_proxy_async();
+      tmem_st_wait();
+      tc_fence_before();
       mbar_arrive(&bars[P_FULL]);
       if (threadIdx.x == 0) TRACE(4, j, 5);
       // O_acc = O_acc * alpha + (P V)[:, this thread's 32 columns]
@@ -250,7 +257,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
       tc_fence_after();
       {
         float v[32];
-        tmem_ld32(t_lane + 128 + half * 32, v);
+        tmem_ld32(t_lane + kColO + half * 32, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] = fmaf(acc[i], alpha, v[i]);
       }
@@ -448,7 +455,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
     // dQ_i: TMEM -> registers -> shared -> TMA reduce-add into dq, with NO block-wide synchronisation: warp w owns rows
     // [32(w%4), +32) of the [128 rows][32 fp32] SWIZZLE_128B block of its column half -- a contiguous, 1024-byte aligned
     // 4 KB slice -- and issues its own 32x32 reduce (bulk groups are per thread: lane 0 waits for its previous one).
-    auto flush_dq = [&](int i) {
+    // stage: registers -> shared; issue: after the (single, shared) fence.proxy.async of the tile.
+    auto stage_dq = [&](int i) {
       mbar_wait(&bars[DQ_FULL], i & 1);  // all GEMMs of tile i have retired: dQ_i is complete, P^T/dS^T smem is free
       tc_fence_after();
       if (lane == 0) tma_wait_group_read0();  // this warp's previous reduce has finished READING its slice
@@ -461,7 +469,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         *reinterpret_cast<float4*>(smem + kOffdQ + half * kTileBytes + r * 128 + ((qd ^ (r & 7)) << 4)) = o4;
       }
       tc_fence_before();
-      fence_proxy_async();
+    };
+    auto issue_dq = [&](int i) {  // caller has executed fence.proxy.async after stage_dq
       __syncwarp();
       if (lane == 0) {  // rows beyond N are clipped by the tensor map
         tma_reduce_add_4d(&mdq, smem + kOffdQ + half * kTileBytes + (warp & 3) * 4096, half * 32, i * kBM + (warp & 3) * 32, h, b);
@@ -469,15 +478,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
       }
     };
 
-    float nlse = INFINITY, ndelta = 0.f;  // lse / delta of this thread's query for the NEXT tile (register prefetch)
+    float nlse = INFINITY, ndelta = 0.f;  // -lse / delta of this thread's query for the NEXT tile (register prefetch)
     if (half == 0 && r < N) {
       nlse = lse[bh * N + r];
       ndelta = delta[bh * N + r];
     }
+    const bool dead_row = bias != 0.f;  // padded or masked key: P^T row is exactly zero
+
     for (int i = 0; i < nq; ++i) {
       const int st = i & 1, q0 = i * kBM;
       if (half == 0) {
-        s_lse[st * kBM + r] = nlse;  // +inf -> p = 0 for padded queries
+        s_lse[st * kBM + r] = -nlse;  // stored NEGATED (folds into the FFMA); -inf -> p = 0 for padded queries
         s_delta[st * kBM + r] = ndelta;
         const int qn = q0 + kBM + r;  // issue the next tile's loads now: their latency hides behind this tile's math
         nlse = INFINITY;
@@ -503,12 +514,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
           tc_fence_before();
           mbar_arrive(&bars[ST_FREE]);
         }
-        const float* lrow = s_lse + st * kBM + half * 64 + c * 32;
+        const float* lrow = s_lse + st * kBM + half * 64 + c * 32;    // -lse
         const float* drow = s_delta + st * kBM + half * 64 + c * 32;
 #pragma unroll
         for (int x = 0; x < 32; x += 2) {
-          const float p0 = ex2(fmaf(s[x], scale_log2, bias) - lrow[x]);
-          const float p1 = ex2(fmaf(s[x + 1], scale_log2, bias) - lrow[x + 1]);
+          const float p0 = ex2(fmaf(s[x], scale_log2, lrow[x]));
+          const float p1 = ex2(fmaf(s[x + 1], scale_log2, lrow[x + 1]));
           const float d0 = p0 * (dp[x] - drow[x]);
           const float d1 = p1 * (dp[x + 1] - drow[x + 1]);
           __nv_bfloat162 pp = f2bf(p0, p1), dd = f2bf(d0, d1);
@@ -516,8 +527,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
           dsk[c][x >> 1] = *reinterpret_cast<uint32_t*>(&dd);
         }
       }
+      if (dead_row) {  // rare (tail tile / masked keys): the whole row of P^T and dS^T is zero
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int x = 0; x < 16; ++x) pk[c][x] = dsk[c][x] = 0u;
+      }
       if (threadIdx.x == 0) TRACE(1, i, 3);
-      if (i > 0) flush_dq(i - 1);  // also the point after which the P^T / dS^T shared tiles may be overwritten
+      if (i > 0) stage_dq(i - 1);  // waits for tile i-1's GEMMs: after this the P^T / dS^T shared tiles may be overwritten
       if (threadIdx.x == 0) TRACE(1, i, 4);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -531,12 +548,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
               make_uint4(dsk[c][qd * 4], dsk[c][qd * 4 + 1], dsk[c][qd * 4 + 2], dsk[c][qd * 4 + 3]);
         }
       }
-      fence_proxy_async();
+      fence_proxy_async();  // ONE generic->async proxy fence per tile covers the dQ staging and the P^T / dS^T tiles
       if (threadIdx.x == 0) TRACE(1, i, 5);
       mbar_arrive(&bars[DS_FULL]);
+      if (i > 0) issue_dq(i - 1);
       if (threadIdx.x == 0) TRACE(1, i, 6);
     }
-    flush_dq(nq - 1);
+    stage_dq(nq - 1);
+    fence_proxy_async();
+    issue_dq(nq - 1);
     if (lane == 0) tma_wait_group0();
     // all GEMMs have retired: write this thread's 32 columns of dV and dK for its key row.  The TMEM loads are
     // .sync.aligned (whole warp, converged); only the global stores are predicated on the key being real.
@@ -570,7 +590,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
 template <bool kTma>
 __global__ void __launch_bounds__(128, 1)
 umma_selftest_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUtensorMap mb,
-                     const uint16_t* __restrict__ A, const uint16_t* __restrict__ Bm, float* __restrict__ C, int a_mn, int b_mn) {
+                     const uint16_t* __restrict__ A, const uint16_t* __restrict__ Bm, float* __restrict__ C, int a_mn, int b_mn,
+                     int a_tmem) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + 2 * kSubTileBytes;
@@ -584,7 +605,7 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap ma, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, 128);
+    tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -610,13 +631,30 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap ma, const __grid_consta
     fence_proxy_async();
     __syncthreads();
   }
+  if (a_tmem) {
+    // TS mode: row m of A -> TMEM lane m, columns [128, 192): column c holds elements (2c, 2c+1) of the row
+    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + 128;
+    const uint32_t* arow = reinterpret_cast<const uint32_t*>(A + threadIdx.x * 128);
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[16];
+      for (int x = 0; x < 16; ++x) v[x] = arow[c * 16 + x];
+      tmem_st16(t_row + c * 16, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
     tc_fence_after();
     const uint32_t idesc = make_idesc(128, 128, a_mn != 0, b_mn != 0);
     const uint32_t aA = smem_u32(sA), aB = smem_u32(sB);
-    for (int k = 0; k < 8; ++k)
-      umma_bf16(tmem_base, a_mn ? desc_mnmajor(aA, k) : desc_kmajor(aA, k), b_mn ? desc_mnmajor(aB, k) : desc_kmajor(aB, k),
-                idesc, k > 0);
+    for (int k = 0; k < 8; ++k) {
+      if (a_tmem)
+        umma_bf16_ts(tmem_base, tmem_base + 128 + k * 8, b_mn ? desc_mnmajor(aB, k) : desc_kmajor(aB, k), idesc, k > 0);
+      else
+        umma_bf16(tmem_base, a_mn ? desc_mnmajor(aA, k) : desc_kmajor(aA, k),
+                  b_mn ? desc_mnmajor(aB, k) : desc_kmajor(aB, k), idesc, k > 0);
+    }
     umma_commit(&bars[1]);
   }
   mbar_wait(&bars[1], 0);
@@ -629,7 +667,7 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap ma, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 128);
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -738,8 +776,9 @@ extern "C" int vbx_debug_set_trace(void* dev_ptr) {
 
 extern "C" int vbx_umma_selftest(const uint16_t* a, const uint16_t* b, float* c, int variant, void* stream) {
   VBX_REQUIRE(a && b && c, VBX_E_NULL);
-  VBX_REQUIRE(variant >= 0 && variant < 8, VBX_E_SHAPE);
-  const int b_mn = variant & 1, a_mn = (variant >> 1) & 1, tma = (variant >> 2) & 1;
+  VBX_REQUIRE(variant >= 0 && variant < 16, VBX_E_SHAPE);
+  const int b_mn = variant & 1, a_mn = (variant >> 1) & 1, tma = (variant >> 2) & 1, a_tmem = (variant >> 3) & 1;
+  VBX_REQUIRE(!(a_tmem && a_mn), VBX_E_UNSUPPORTED);  // a TMEM A operand cannot be transposed
   CUtensorMap ma, mb;
   int rc;
   if ((rc = make_tmap(&ma, a, 128, 128, 1, 1, 128, 128 * 128, 128 * 128, 128)) != VBX_OK) return rc;
@@ -748,10 +787,10 @@ extern "C" int vbx_umma_selftest(const uint16_t* a, const uint16_t* b, float* c,
   cudaStream_t s = (cudaStream_t)stream;
   if (tma) {
     cudaFuncSetAttribute(umma_selftest_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    umma_selftest_kernel<true><<<1, 128, smem, s>>>(ma, mb, a, b, c, a_mn, b_mn);
+    umma_selftest_kernel<true><<<1, 128, smem, s>>>(ma, mb, a, b, c, a_mn, b_mn, a_tmem);
   } else {
     cudaFuncSetAttribute(umma_selftest_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    umma_selftest_kernel<false><<<1, 128, smem, s>>>(ma, mb, a, b, c, a_mn, b_mn);
+    umma_selftest_kernel<false><<<1, 128, smem, s>>>(ma, mb, a, b, c, a_mn, b_mn, a_tmem);
   }
   return VBX_LAUNCH_RC();
 }
