@@ -197,13 +197,18 @@ def main():
     x_host = torch.randn(B, N, D).pin_memory()
     x_dev = x_host.to(dev)
 
+    found_inf = torch.zeros((), device=dev)
+
     def train_step(x):
         bucket.zero_grad()
         loss = w(x)                                   # ConditionalFlowMatcherWrapper.forward (public API)
         loss.backward()                               # chunked all-reduce overlaps with this (N>1)
         bucket.finish()
-        gnorm = bucket.flat.norm()                    # clip_grad_norm_(0.5), trainer.py:274-275, on the flat bucket
-        bucket.flat.mul_(torch.clamp(0.5 / (gnorm + 1e-6), max=1.0))
+        gnorm = bucket.flat.norm()                    # clip_grad_norm_(0.5), trainer.py:274-275, on the flat bucket:
+        # the clip coefficient c = min(1, 0.5/(norm+1e-6)) is applied INSIDE the fused Adam kernel (its grad_scale input
+        # divides every gradient by 1/c) instead of a separate 2 x 2.85 GB scaling pass
+        opt.grad_scale = torch.clamp((gnorm + 1e-6) / 0.5, min=1.0)
+        opt.found_inf = found_inf
         opt.step()
         return loss
 

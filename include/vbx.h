@@ -66,7 +66,9 @@ int vbx_adarms_bwd(const float* x, int64_t x_batch_stride, int64_t row0, const f
  *   h: bf16 [T, 2*Fp], value = h[:, :Fp], gate = h[:, Fp:]  ->  out bf16 [T, Fp] = gelu_erf(gate) * value
  * Fp is the feed-forward inner width zero-padded to a multiple of 8 by the caller (exact: gelu(0)*0 = 0). */
 int vbx_geglu_fwd(const uint16_t* h, uint16_t* out, int64_t T, int64_t Fp, void* stream);
-int vbx_geglu_bwd(const uint16_t* h, const uint16_t* dout, uint16_t* dh, int64_t T, int64_t Fp, void* stream);
+/* dbias (f32 [2*Fp], may be NULL, ACCUMULATED: caller zeroes): column sums of dh, i.e. the bias gradient of the Linear that
+ * produced h (vp.py:345) -- saves the separate reduction pass over dh. */
+int vbx_geglu_bwd(const uint16_t* h, const uint16_t* dout, uint16_t* dh, float* dbias, int64_t T, int64_t Fp, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Conv positional embedding + residual + register-token pack      replaces vp.py:203-233 (+ caller's `+ x`, :826/:1080)

@@ -116,6 +116,50 @@ def test_geglu_fwd_bwd(vbx, T, Fp):
     assert rel_err(h1.grad, hr.grad) < 2 ** -8
 
 
+def test_linear_geglu_fused_node_bias_grad(vbx):
+    """FF1 + GEGLU as one autograd node (vp.py:345-346): the Linear's bias gradient comes out of the GEGLU backward kernel
+    (fp32 column sums of the bf16-rounded dh) instead of a separate reduction; dx / dw are the usual bf16 GEMMs."""
+    torch.manual_seed(7)
+    T, D, Fp = 520, 128, 192
+    x = torch.randn(2, T // 2, D, device='cuda').to(BF16)
+    w = (torch.randn(2 * Fp, D, device='cuda') * 0.1).to(BF16)
+    b = (torch.randn(2 * Fp, device='cuda') * 0.1).to(BF16)
+    xr, wr, br = (t.float().requires_grad_() for t in (x, w, b))
+    lin = torch.nn.functional.linear(xr, wr, br)
+    hr = lin + (rbf(lin) - lin).detach()                        # the GEMM output is bf16 in both paths (straight-through)
+    val, gate = hr.chunk(2, dim=-1)
+    ref = torch.nn.functional.gelu(gate) * val
+    x1, w1, b1 = (t.clone().requires_grad_() for t in (x, w, b))
+    out = vbx.ops.linear_geglu(x1, w1, b1)
+    assert rel_err(out, ref) < 2 ** -7
+    d = torch.randn_like(ref).to(BF16)
+    ref.backward(d.float())
+    out.backward(d)
+    assert rel_err(b1.grad, br.grad) < 2e-2      # bf16 storage of the result; sums over 520 rows of bf16-rounded terms
+    assert rel_err(w1.grad, wr.grad) < 2e-2
+    assert rel_err(x1.grad, xr.grad) < 2e-2
+
+
+def test_clip_coefficient_through_fused_adam_grad_scale():
+    """bench.py applies clip_grad_norm_(0.5) (trainer.py:274-275) through the fused Adam kernel's grad_scale input: identical to
+    scaling the gradients first."""
+    torch.manual_seed(8)
+    p1 = torch.randn(1000, device='cuda', requires_grad=True)
+    p2 = p1.detach().clone().requires_grad_()
+    g = torch.randn(1000, device='cuda') * 3
+    o1 = torch.optim.Adam([p1], lr=3e-4, betas=(0.9, 0.99), fused=True)
+    o2 = torch.optim.Adam([p2], lr=3e-4, betas=(0.9, 0.99), fused=True)
+    for _ in range(3):
+        norm = g.norm()
+        p1.grad = g * torch.clamp(0.5 / (norm + 1e-6), max=1.0)
+        o1.step()
+        p2.grad = g.clone()
+        o2.grad_scale = torch.clamp((norm + 1e-6) / 0.5, min=1.0)
+        o2.found_inf = torch.zeros((), device='cuda')
+        o2.step()
+    assert torch.allclose(p1, p2, rtol=1e-6, atol=1e-7)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('B,N,C,K,R,masked', [(2, 200, 128, 31, 16, False), (3, 100, 128, 31, 0, True), (2, 300, 64, 7, 4, True),
                                               (1, 1024, 256, 31, 16, False)])

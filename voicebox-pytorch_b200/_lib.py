@@ -18,7 +18,7 @@ _SIGNATURES = {
     'vbx_adarms_fwd': [_vp, _i64, _i64, _vp, _vp, _vp, _int, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
     'vbx_adarms_bwd': [_vp, _i64, _i64, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
     'vbx_geglu_fwd': [_vp, _vp, _i64, _i64, _vp],
-    'vbx_geglu_bwd': [_vp, _vp, _vp, _i64, _i64, _vp],
+    'vbx_geglu_bwd': [_vp, _vp, _vp, _vp, _i64, _i64, _vp],
     'vbx_convpos_fwd': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp],
     'vbx_convpos_bwd': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp],
     'vbx_cfm_embed': [_vp, _vp, _vp, _vp, _f32, _vp, _i64, _i64, _i64, _vp],

@@ -82,10 +82,20 @@ VBX_DEVINL float warp_sum(float v) {
 // of the reference (nn.GELU(), F.gelu default) is reproduced to ~2e-7 absolute, far inside the bf16 output ulp, at a
 // third of erff()'s instruction count, which keeps the GEGLU / conv passes HBM-bound instead of issue-bound.
 // Returns Phi(x) = 0.5*(1+erf(x/sqrt2)) and e = exp(-x^2/2).
+VBX_DEVINL float rcp_approx(float x) {  // MUFU.RCP, rel err 2^-23; __frcp_rn would add Newton steps + a slow-path CALL
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+VBX_DEVINL float ex2_approx(float x) {  // MUFU.EX2, rel err 2^-22; exp2f() adds denormal range handling
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 VBX_DEVINL float normal_cdf(float x, float& e) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  e = exp2f(-1.4426950408889634f * z * z);
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  e = ex2_approx(-1.4426950408889634f * z * z);
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);

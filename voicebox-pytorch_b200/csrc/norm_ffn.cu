@@ -180,42 +180,93 @@ __global__ void __launch_bounds__(256, 2) adarms_bwd_kernel(const float* __restr
 // ------------------------------------------------------------------------------------------------------------------
 // GEGLU: out = gelu_erf(gate) * value, value = h[:, :Fp], gate = h[:, Fp:]
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) geglu_fwd_kernel(const uint16_t* __restrict__ h, uint16_t* __restrict__ out, int64_t T,
+// Thread layout for both GEGLU kernels: threadIdx/blockIdx.x pick a fixed 8-element column vector, blockIdx.y strides the
+// rows -- no integer division anywhere (a 64-bit div per grid-stride iteration made the first version issue-bound), and
+// four rows are in flight per thread.
+constexpr int kGegluRowsUnroll = 4;
+
+__global__ void __launch_bounds__(128) geglu_fwd_kernel(const uint16_t* __restrict__ h, uint16_t* __restrict__ out, int64_t T,
                                                          int Fp) {
-  const int vec_per_row = Fp >> 3;
-  const int64_t total = T * vec_per_row;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t t = i / vec_per_row;
-    const int c = (int)(i - t * vec_per_row) << 3;
-    float val[8], gate[8], o[8];
-    unpack8(ldg_nc_16(h + t * 2 * Fp + c), val);
-    unpack8(ldg_nc_16(h + t * 2 * Fp + Fp + c), gate);
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) << 3;
+  if (c >= Fp) return;
+  const int64_t row_stride = (int64_t)gridDim.y * kGegluRowsUnroll;
+  for (int64_t t0 = (int64_t)blockIdx.y * kGegluRowsUnroll; t0 < T; t0 += row_stride) {
+    uint4 uv[kGegluRowsUnroll], ug[kGegluRowsUnroll];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = gelu_f(gate[k]) * val[k];
-    stg_16(out + t * Fp + c, pack8(o));
+    for (int u = 0; u < kGegluRowsUnroll; ++u) {
+      if (t0 + u < T) {
+        uv[u] = ldg_nc_16(h + (t0 + u) * 2 * Fp + c);
+        ug[u] = ldg_nc_16(h + (t0 + u) * 2 * Fp + Fp + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kGegluRowsUnroll; ++u) {
+      if (t0 + u < T) {
+        float val[8], gate[8], o[8];
+        unpack8(uv[u], val);
+        unpack8(ug[u], gate);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = gelu_f(gate[k]) * val[k];
+        stg_16(out + (t0 + u) * Fp + c, pack8(o));
+      }
+    }
   }
 }
 
-__global__ void __launch_bounds__(256) geglu_bwd_kernel(const uint16_t* __restrict__ h, const uint16_t* __restrict__ dout,
-                                                         uint16_t* __restrict__ dh, int64_t T, int Fp) {
-  const int vec_per_row = Fp >> 3;
-  const int64_t total = T * vec_per_row;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t t = i / vec_per_row;
-    const int c = (int)(i - t * vec_per_row) << 3;
-    float val[8], gate[8], d[8], dv[8], dg[8];
-    unpack8(ldg_nc_16(h + t * 2 * Fp + c), val);
-    unpack8(ldg_nc_16(h + t * 2 * Fp + Fp + c), gate);
-    unpack8(ldg_nc_16(dout + t * Fp + c), d);
+// dbias (f32 [2*Fp], may be NULL): column sums of dh = the bias gradient of the Linear that produced h (vp.py:345).  The
+// thread <-> column mapping is fixed, so the sums live in 16 registers and cost one atomic per column per thread at the end
+// -- instead of a separate reduction pass re-reading all of dh (733 MB per layer at cfg3).
+__global__ void __launch_bounds__(128) geglu_bwd_kernel(const uint16_t* __restrict__ h, const uint16_t* __restrict__ dout,
+                                                         uint16_t* __restrict__ dh, float* __restrict__ dbias, int64_t T, int Fp) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) << 3;
+  if (c >= Fp) return;
+  float sv[8], sg[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sv[k] = sg[k] = 0.f;
+  const int64_t row_stride = (int64_t)gridDim.y * kGegluRowsUnroll;
+  for (int64_t t0 = (int64_t)blockIdx.y * kGegluRowsUnroll; t0 < T; t0 += row_stride) {
+    uint4 uv[kGegluRowsUnroll], ug[kGegluRowsUnroll], ud[kGegluRowsUnroll];
+#pragma unroll
+    for (int u = 0; u < kGegluRowsUnroll; ++u) {
+      if (t0 + u < T) {
+        uv[u] = ldg_nc_16(h + (t0 + u) * 2 * Fp + c);
+        ug[u] = ldg_nc_16(h + (t0 + u) * 2 * Fp + Fp + c);
+        ud[u] = ldg_nc_16(dout + (t0 + u) * Fp + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kGegluRowsUnroll; ++u) {
+      if (t0 + u < T) {
+        float val[8], gate[8], d[8], dv[8], dg[8];
+        unpack8(uv[u], val);
+        unpack8(ug[u], gate);
+        unpack8(ud[u], d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float e;
+          const float cdf = normal_cdf(gate[k], e);
+          dv[k] = d[k] * gate[k] * cdf;                                         // d value
+          dg[k] = d[k] * val[k] * fmaf(gate[k] * 0.3989422804014327f, e, cdf);  // d gate
+        }
+        const uint4 pv = pack8(dv), pg = pack8(dg);
+        stg_16(dh + (t0 + u) * 2 * Fp + c, pv);
+        stg_16(dh + (t0 + u) * 2 * Fp + Fp + c, pg);
+        if (dbias != nullptr) {  // sum what was actually stored (bf16-rounded), as a reduction over dh would
+          float rv[8], rg[8];
+          unpack8(pv, rv);
+          unpack8(pg, rg);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) sv[k] += rv[k], sg[k] += rg[k];
+        }
+      }
+    }
+  }
+  if (dbias != nullptr) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float e;
-      const float cdf = normal_cdf(gate[k], e);
-      dv[k] = d[k] * gate[k] * cdf;                                                   // d value
-      dg[k] = d[k] * val[k] * fmaf(gate[k] * 0.3989422804014327f, e, cdf);            // d gate
+      atomicAdd(dbias + c + k, sv[k]);
+      atomicAdd(dbias + Fp + c + k, sg[k]);
     }
-    stg_16(dh + t * 2 * Fp + c, pack8(dv));
-    stg_16(dh + t * 2 * Fp + Fp + c, pack8(dg));
   }
 }
 
@@ -290,14 +341,23 @@ extern "C" int vbx_geglu_fwd(const uint16_t* h, uint16_t* out, int64_t T, int64_
   VBX_REQUIRE(h && out, VBX_E_NULL);
   VBX_REQUIRE(T > 0 && Fp > 0 && Fp % 8 == 0, VBX_E_SHAPE);
   VBX_REQUIRE(VBX_ALIGNED16(h) && VBX_ALIGNED16(out), VBX_E_ALIGN);
-  geglu_fwd_kernel<<<grid_for(T * (Fp / 8), 256, 8), 256, 0, (cudaStream_t)stream>>>(h, out, T, (int)Fp);
+  const unsigned gx = (unsigned)((Fp / 8 + 127) / 128);
+  int64_t gy = (T + kGegluRowsUnroll - 1) / kGegluRowsUnroll;
+  const int64_t cap = (int64_t)kNumSM * 16 / gx + 1;  // ~16 CTAs of 128 threads per SM in flight, then stride
+  if (gy > cap) gy = cap;
+  geglu_fwd_kernel<<<dim3(gx, (unsigned)gy), 128, 0, (cudaStream_t)stream>>>(h, out, T, (int)Fp);
   return VBX_LAUNCH_RC();
 }
 
-extern "C" int vbx_geglu_bwd(const uint16_t* h, const uint16_t* dout, uint16_t* dh, int64_t T, int64_t Fp, void* stream) {
+extern "C" int vbx_geglu_bwd(const uint16_t* h, const uint16_t* dout, uint16_t* dh, float* dbias, int64_t T, int64_t Fp,
+                             void* stream) {
   VBX_REQUIRE(h && dout && dh, VBX_E_NULL);
   VBX_REQUIRE(T > 0 && Fp > 0 && Fp % 8 == 0, VBX_E_SHAPE);
   VBX_REQUIRE(VBX_ALIGNED16(h) && VBX_ALIGNED16(dout) && VBX_ALIGNED16(dh), VBX_E_ALIGN);
-  geglu_bwd_kernel<<<grid_for(T * (Fp / 8), 256, 8), 256, 0, (cudaStream_t)stream>>>(h, dout, dh, T, (int)Fp);
+  const unsigned gx = (unsigned)((Fp / 8 + 127) / 128);
+  int64_t gy = (T + kGegluRowsUnroll - 1) / kGegluRowsUnroll;
+  const int64_t cap = (int64_t)kNumSM * (dbias ? 6 : 16) / gx + 1;  // fewer, longer threads when they end in atomics
+  if (gy > cap) gy = cap;
+  geglu_bwd_kernel<<<dim3(gx, (unsigned)gy), 128, 0, (cudaStream_t)stream>>>(h, dout, dh, dbias, T, (int)Fp);
   return VBX_LAUNCH_RC();
 }

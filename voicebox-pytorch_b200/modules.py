@@ -264,7 +264,7 @@ def _ff_branch(ff, h):
         w1 = ops.cast_bf16(lin1.weight, 'w1p', pad_w1)
         b1 = ops.cast_bf16(lin1.bias, 'b1p', pad_w1)
         w2 = ops.cast_bf16(lin2.weight, 'w2p', lambda w: F.pad(w, (0, fp - f)))
-    g = ops.geglu(F.linear(h, w1, b1))
+    g = ops.linear_geglu(h, w1, b1)
     return F.linear(g, w2, ops.cast_bf16(lin2.bias, 'b'))
 
 
@@ -345,6 +345,7 @@ def transformer_trunk(self, x, mask, cond, n_out):
         return norm.gamma, None
 
     has_skips = any(exists(layer[0]) for layer in self.layers)
+    inplace = inplace and not has_skips  # saved skip tensors must survive the later residual updates
     pending = None  # bf16 branch output not yet added to the residual stream (fused into the next norm kernel)
     skips = []
     for skip_combiner, gateloop, attn_norm, attn, ff_norm, ff in self.layers:

@@ -144,13 +144,49 @@ class _Geglu(torch.autograd.Function):
         dout = _c(dout)
         T, two_f = h.numel() // h.shape[-1], h.shape[-1]
         dh = torch.empty_like(h)
-        call('vbx_geglu_bwd', ptr(h), ptr(dout), ptr(dh), T, two_f // 2, stream())
+        call('vbx_geglu_bwd', ptr(h), ptr(dout), ptr(dh), None, T, two_f // 2, stream())
         return dh
 
 
 def geglu(h):
     """h bf16 [..., 2*Fp] (value | gate) -> gelu_erf(gate) * value, bf16 [..., Fp]   (vp.py:337-340)."""
     return _Geglu.apply(h)
+
+
+class _LinearGeglu(torch.autograd.Function):
+    """g = GEGLU(x @ w^T + b)  (vp.py:345-346) as ONE autograd node: the backward gets the Linear's bias gradient as a by-product
+    of the GEGLU backward kernel (column sums of dh held in registers) instead of a separate reduction pass over dh."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        shp = x.shape
+        x2 = _c(x.reshape(-1, shp[-1]))
+        h = F.linear(x2, w, b)                     # bf16 library GEMM [T, 2Fp]
+        T, two_f = h.shape
+        out = torch.empty((T, two_f // 2), device=h.device, dtype=BF16)
+        call('vbx_geglu_fwd', ptr(h), ptr(out), T, two_f // 2, stream())
+        ctx.save_for_backward(x2, w, h)
+        ctx.shp = shp
+        return out.reshape(shp[:-1] + (two_f // 2,))
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, w, h = ctx.saved_tensors
+        T, two_f = h.shape
+        dout = _c(dout.reshape(T, two_f // 2))
+        dh = torch.empty_like(h)
+        db = torch.zeros((two_f,), device=h.device, dtype=torch.float32)
+        call('vbx_geglu_bwd', ptr(h), ptr(dout), ptr(dh), ptr(db), T, two_f // 2, stream())
+        dx = (dh @ w).reshape(ctx.shp) if ctx.needs_input_grad[0] else None
+        dw = dh.t() @ x2 if ctx.needs_input_grad[1] else None
+        return dx, dw, db.to(BF16) if ctx.needs_input_grad[2] else None
+
+
+def linear_geglu(x, w_bf16, b_bf16):
+    """x bf16 [..., D], w bf16 [2Fp, D], b bf16 [2Fp] -> bf16 [..., Fp]."""
+    if torch.is_grad_enabled() and (x.requires_grad or w_bf16.requires_grad or b_bf16.requires_grad):
+        return _LinearGeglu.apply(x, w_bf16, b_bf16)
+    return geglu(F.linear(x, w_bf16, b_bf16))
 
 
 # ---------------------------------------------------------------------------------------------------------------------
