@@ -132,35 +132,45 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
     }
   } else if (warp == 9) {
     // ------------------------------------------------ MMA issuer --------------------------------------------------
-    if (lane == 0) {
+    // Warp-uniform control flow: all 32 lanes run the loop and the barrier waits, so the descriptors (hoisted out of the
+    // loop, per-K-step constants added) stay in uniform registers; only tcgen05.mma / commit are issued by the leader lane.
+    {
       constexpr uint32_t idesc_s = make_idesc(kBM, kBN, false, false);  // S = Q K^T      (both K-major)
       constexpr uint32_t idesc_o = make_idesc(kBM, kDh, false, true);   // O = P V        (V is MN-major: [keys][d])
-      const uint32_t aQ = smem_u32(smem + kOffQ);
+      const uint64_t dQ = sdesc_k0(smem_u32(smem + kOffQ));
+      const uint64_t dK0 = sdesc_k0(smem_u32(smem + kOffK)), dV0 = sdesc_mn0(smem_u32(smem + kOffV));
+      const bool leader = lane == 0;
       mbar_wait(&bars[Q_FULL], 0);
       for (int j = 0; j < nkv; ++j) {
         const int st = j & 1;
-        const uint32_t aK = smem_u32(smem + kOffK + st * kTileBytes), aV = smem_u32(smem + kOffV + st * kTileBytes);
+        const uint64_t dK = dK0 + (uint64_t)st * (kTileBytes >> 4), dV = dV0 + (uint64_t)st * (kTileBytes >> 4);
         TRACE(3, j, 0);
         mbar_wait(&bars[K_FULL + st], (j >> 1) & 1);
         TRACE(3, j, 1);
         mbar_wait(&bars[S_FREE], (j & 1) ^ 1);
         TRACE(3, j, 2);
         tc_fence_after();
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < kDh / 16; ++k) umma_bf16(tmem_base, desc_kmajor(aQ, k), desc_kmajor(aK, k), idesc_s, k > 0);
-        umma_commit(&bars[S_FULL]);
-        umma_commit(&bars[K_EMPTY + st]);
+          for (int k = 0; k < kDh / 16; ++k) umma_bf16(tmem_base, dQ + koff_k(k), dK + koff_k(k), idesc_s, k > 0);
+          umma_commit(&bars[S_FULL]);
+          umma_commit(&bars[K_EMPTY + st]);
+        }
+        __syncwarp();
         TRACE(3, j, 3);
         mbar_wait(&bars[V_FULL + st], (j >> 1) & 1);
         TRACE(3, j, 4);
         mbar_wait(&bars[P_FULL], j & 1);
         TRACE(3, j, 5);
         tc_fence_after();
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < kBN / 16; ++k)  // A = P from TMEM: 8 columns (16 keys) per K-step
-          umma_bf16_ts(tmem_base + kColO, tmem_base + kColP + k * 8, desc_mnmajor(aV, k), idesc_o, k > 0);
-        umma_commit(&bars[O_FULL]);
-        umma_commit(&bars[V_EMPTY + st]);
+          for (int k = 0; k < kBN / 16; ++k)  // A = P from TMEM: 8 columns (16 keys) per K-step
+            umma_bf16_ts(tmem_base + kColO, tmem_base + kColP + k * 8, dV + koff_mn(k), idesc_o, k > 0);
+          umma_commit(&bars[O_FULL]);
+          umma_commit(&bars[V_EMPTY + st]);
+        }
+        __syncwarp();
         TRACE(3, j, 6);
       }
     }
@@ -317,13 +327,13 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const uint16_t* __restr
 }
 namespace bwd {
 constexpr int kStages = 3;  // Q/dO ring: the load of tile i+2 is issued as soon as the GEMMs of tile i-1 retire
-constexpr uint32_t kOffK = 0, kOffV = 16384, kOffQ = 32768, kOffdO = kOffQ + kStages * 16384, kOffPT = kOffdO + kStages * 16384,
-                   kOffdST = kOffPT + 32768, kOffdQ = kOffdST + 32768, kOffBar = kOffdQ + 32768, kOffLse = kOffBar + 128,
-                   kOffDelta = kOffLse + 2 * kBM * 4;
-constexpr uint32_t kSmemBytes = kOffDelta + 2 * kBM * 4;  // 231,552 B of the 232,448 B a CTA may use: one CTA per SM
+constexpr uint32_t kOffK = 0, kOffV = 16384, kOffQ = 32768, kOffdO = kOffQ + kStages * 16384,
+                   kOffdST = kOffdO + kStages * 16384, kOffdQ = kOffdST + 32768, kOffBar = kOffdQ + 32768,
+                   kOffLse = kOffBar + 128, kOffDelta = kOffLse + 2 * kBM * 4;
+constexpr uint32_t kSmemBytes = kOffDelta + 2 * kBM * 4;  // 198,784 B: one CTA per SM (TMEM: all 512 columns)
 enum { KV_FULL = 0, QD_FULL = 1, QD_EMPTY = 4, ST_FULL = 7, ST_FREE = 8, DS_FULL = 9, DQ_FULL = 10, NUM_BARS = 11 };
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColST = 0, kColDPT = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
+constexpr uint32_t kColST = 0, kColDPT = 128, kColDV = 256, kColDK = 320, kColDQ = 384, kColPT = 448;  // P^T: bf16 pairs
 constexpr int kThreads = 320;
 }  // namespace bwd
 
@@ -395,51 +405,61 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
+    // warp-uniform control flow, hoisted descriptors (see the forward kernel): only the leader lane issues MMAs / commits
+    {
       constexpr uint32_t idesc_kk = make_idesc(128, 128, false, false);
       constexpr uint32_t idesc_kmn = make_idesc(128, kDh, false, true);
       constexpr uint32_t idesc_mnmn = make_idesc(128, kDh, true, true);
-      const uint32_t aK = smem_u32(smem + kOffK), aV = smem_u32(smem + kOffV), aPT = smem_u32(smem + kOffPT),
-                     aDST = smem_u32(smem + kOffdST);
+      const bool leader = lane == 0;
+      const uint64_t dKk = sdesc_k0(smem_u32(smem + kOffK)), dKmn = sdesc_mn0(smem_u32(smem + kOffK));
+      const uint64_t dVk = sdesc_k0(smem_u32(smem + kOffV));
+      const uint64_t dQk0 = sdesc_k0(smem_u32(smem + kOffQ)), dQmn0 = sdesc_mn0(smem_u32(smem + kOffQ));
+      const uint64_t dOk0 = sdesc_k0(smem_u32(smem + kOffdO)), dOmn0 = sdesc_mn0(smem_u32(smem + kOffdO));
+      const uint64_t dSk = sdesc_k0(smem_u32(smem + kOffdST)), dSmn = sdesc_mn0(smem_u32(smem + kOffdST));
       auto issue_s = [&](int i) {  // S^T = K Q_i^T, dP^T = V dO_i^T
-        const int st = i % kStages;
-        const uint32_t aQ = smem_u32(smem + kOffQ + st * kTileBytes), aDO = smem_u32(smem + kOffdO + st * kTileBytes);
+        const uint64_t so = (uint64_t)(i % kStages) * (kTileBytes >> 4);
         TRACE(0, i, 0);
-        mbar_wait(&bars[QD_FULL + st], (i / kStages) & 1);
+        mbar_wait(&bars[QD_FULL + i % kStages], (i / kStages) & 1);
         TRACE(0, i, 1);
         mbar_wait(&bars[ST_FREE], (i & 1) ^ 1);  // the compute warps hold tile i-1's S^T/dP^T in registers
         TRACE(0, i, 2);
         tc_fence_after();
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < kDh / 16; ++k)
-          umma_bf16(tmem_base + kColST, desc_kmajor(aK, k), desc_kmajor(aQ, k), idesc_kk, k > 0);
+          for (int k = 0; k < kDh / 16; ++k)
+            umma_bf16(tmem_base + kColST, dKk + koff_k(k), dQk0 + so + koff_k(k), idesc_kk, k > 0);
 #pragma unroll
-        for (int k = 0; k < kDh / 16; ++k)
-          umma_bf16(tmem_base + kColDPT, desc_kmajor(aV, k), desc_kmajor(aDO, k), idesc_kk, k > 0);
-        umma_commit(&bars[ST_FULL]);
+          for (int k = 0; k < kDh / 16; ++k)
+            umma_bf16(tmem_base + kColDPT, dVk + koff_k(k), dOk0 + so + koff_k(k), idesc_kk, k > 0);
+          umma_commit(&bars[ST_FULL]);
+        }
+        __syncwarp();
         TRACE(0, i, 3);
       };
       mbar_wait(&bars[KV_FULL], 0);
       issue_s(0);
       for (int i = 0; i < nq; ++i) {
         const int st = i % kStages;
-        const uint32_t aQ = smem_u32(smem + kOffQ + st * kTileBytes), aDO = smem_u32(smem + kOffdO + st * kTileBytes);
+        const uint64_t so = (uint64_t)st * (kTileBytes >> 4);
         if (i + 1 < nq) issue_s(i + 1);  // runs on the tensor pipe while the compute warps finish tile i
         TRACE(0, i, 4);
         mbar_wait(&bars[DS_FULL], i & 1);
         TRACE(0, i, 5);
         tc_fence_after();
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < kBM / 16; ++k)  // dV += P^T dO
-          umma_bf16(tmem_base + kColDV, desc_kmajor(aPT, k), desc_mnmajor(aDO, k), idesc_kmn, (i > 0) || (k > 0));
+          for (int k = 0; k < kBM / 16; ++k)  // dV += P^T dO   (TS mode: P^T read from TMEM, only dO from shared memory)
+            umma_bf16_ts(tmem_base + kColDV, tmem_base + kColPT + k * 8, dOmn0 + so + koff_mn(k), idesc_kmn, (i > 0) || (k > 0));
 #pragma unroll
-        for (int k = 0; k < kBM / 16; ++k)  // dK += dS^T Q
-          umma_bf16(tmem_base + kColDK, desc_kmajor(aDST, k), desc_mnmajor(aQ, k), idesc_kmn, (i > 0) || (k > 0));
+          for (int k = 0; k < kBM / 16; ++k)  // dK += dS^T Q
+            umma_bf16(tmem_base + kColDK, dSk + koff_k(k), dQmn0 + so + koff_mn(k), idesc_kmn, (i > 0) || (k > 0));
 #pragma unroll
-        for (int k = 0; k < kBN / 16; ++k)  // dQ_i = dS K    (A = dS^T read MN-major)
-          umma_bf16(tmem_base + kColDQ, desc_mnmajor(aDST, k), desc_mnmajor(aK, k), idesc_mnmn, k > 0);
-        umma_commit(&bars[DQ_FULL]);
-        umma_commit(&bars[QD_EMPTY + st]);
+          for (int k = 0; k < kBN / 16; ++k)  // dQ_i = dS K    (A = dS^T read MN-major)
+            umma_bf16(tmem_base + kColDQ, dSmn + koff_mn(k), dKmn + koff_mn(k), idesc_mnmn, k > 0);
+          umma_commit(&bars[DQ_FULL]);
+          umma_commit(&bars[QD_EMPTY + st]);
+        }
+        __syncwarp();
         TRACE(0, i, 6);
       }
     }
@@ -536,19 +556,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
       if (threadIdx.x == 0) TRACE(1, i, 3);
       if (i > 0) stage_dq(i - 1);  // waits for tile i-1's GEMMs: after this the P^T / dS^T shared tiles may be overwritten
       if (threadIdx.x == 0) TRACE(1, i, 4);
+      // P^T -> TMEM (A operand of the TS-mode dV GEMM: never touches shared memory); dS^T -> shared (K-major for dK, and
+      // read MN-major for dQ)
+      tmem_st16(t_lane + kColPT + half * 32, pk[0]);
+      tmem_st16(t_lane + kColPT + half * 32 + 16, pk[1]);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
           const int cc = c * 4 + qd;  // 16-byte chunk inside this half's 64-query sub-tile
           const uint32_t off = half * kSubTileBytes + r * 128 + ((cc ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(smem + kOffPT + off) =
-              make_uint4(pk[c][qd * 4], pk[c][qd * 4 + 1], pk[c][qd * 4 + 2], pk[c][qd * 4 + 3]);
           *reinterpret_cast<uint4*>(smem + kOffdST + off) =
               make_uint4(dsk[c][qd * 4], dsk[c][qd * 4 + 1], dsk[c][qd * 4 + 2], dsk[c][qd * 4 + 3]);
         }
       }
-      fence_proxy_async();  // ONE generic->async proxy fence per tile covers the dQ staging and the P^T / dS^T tiles
+      tmem_st_wait();
+      tc_fence_before();
+      fence_proxy_async();  // ONE generic->async proxy fence per tile covers the dQ staging and the dS^T tile
       if (threadIdx.x == 0) TRACE(1, i, 5);
       mbar_arrive(&bars[DS_FULL]);
       if (i > 0) issue_dq(i - 1);
@@ -769,6 +793,75 @@ extern "C" int vbx_attn_bwd(const uint16_t* q, const uint16_t* k, const uint16_t
 }
 
 #ifdef VBX_TRACE
+// ---- MMA throughput microbenchmark (trace build only): cycles for `iters` x 8 back-to-back MMAs of one configuration ----
+namespace vbx {
+template <int NACC, bool ATMEM>
+__global__ void __launch_bounds__(128, 1) umma_bench_kernel(long long* out, int n, int a_mn, int b_mn, int iters) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 4 * kSubTileBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 4 * (int)kSubTileBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = *tmem_slot;
+  if (warp == 1) {  // warp-uniform issue loop, leader lane issues
+    const uint32_t idesc = make_idesc(128, n, a_mn != 0, b_mn != 0);
+    const uint64_t a0 = a_mn ? sdesc_mn0(smem_u32(smem)) : sdesc_k0(smem_u32(smem));
+    const uint64_t b0 = b_mn ? sdesc_mn0(smem_u32(smem + 2 * kSubTileBytes)) : sdesc_k0(smem_u32(smem + 2 * kSubTileBytes));
+    const uint64_t as = a_mn ? koff_mn(1) : 2, bs = b_mn ? koff_mn(1) : 2;
+    const bool leader = (threadIdx.x & 31) == 0;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // accumulators rotate over NACC independent TMEM tiles (compile-time addresses)
+          const uint32_t d = tb + (uint32_t)(k % NACC) * 64;
+          if (ATMEM) umma_bf16_ts(d, tb + 256 + (k & 3) * 8, b0 + (k & 3) * bs, idesc, 1);
+          else umma_bf16(d, a0 + (k & 3) * as, b0 + (k & 3) * bs, idesc, 1);
+        }
+      }
+      __syncwarp();
+    }
+    const long long t1 = clock64();
+    if (leader) umma_commit(&bars[0]);
+    mbar_wait(&bars[0], 0);
+    const long long t2 = clock64();
+    if (leader) {
+      out[0] = t1 - t0;  // issue time
+      out[1] = t2 - t0;  // until all retired
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+}  // namespace vbx
+extern "C" int vbx_debug_umma_bench(long long* out, int n, int a_mn, int b_mn, int a_tmem, int iters, int ctas, int nacc) {
+  const int smem = 4 * ptx::kSubTileBytes + 64;
+#define VBX_BENCH(NA, AT)                                                                                         \
+  {                                                                                                               \
+    cudaFuncSetAttribute(vbx::umma_bench_kernel<NA, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);      \
+    vbx::umma_bench_kernel<NA, AT><<<ctas, 128, smem>>>(out, n, a_mn, b_mn, iters);                               \
+  }
+  if (a_tmem) {
+    if (nacc == 1) VBX_BENCH(1, true) else if (nacc == 2) VBX_BENCH(2, true) else VBX_BENCH(4, true)
+  } else {
+    if (nacc == 1) VBX_BENCH(1, false) else if (nacc == 2) VBX_BENCH(2, false) else VBX_BENCH(4, false)
+  }
+#undef VBX_BENCH
+  return (int)cudaGetLastError();
+}
 extern "C" int vbx_debug_set_trace(void* dev_ptr) {
   return (int)cudaMemcpyToSymbol(vbx::g_trace, &dev_ptr, sizeof(void*));
 }

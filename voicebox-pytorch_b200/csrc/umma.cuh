@@ -159,6 +159,14 @@ VBX_DEVINL uint64_t desc_mnmajor(uint32_t tile_addr, int kstep) {
   return make_sdesc(tile_addr + (uint32_t)kstep * 2048, kSubTileBytes, 1024);
 }
 
+// Hoisted forms: build the descriptor of K-step 0 once per operand tile, then ADD a compile-time constant per K-step (the
+// start-address field is the low 14 bits, in 16-byte units; shared memory is < 256 KB so the add never carries out of it).
+// Rebuilding the full descriptor per MMA costs a ~90-clk dependent scalar chain in the issuing thread -- more than the MMA.
+VBX_DEVINL uint64_t sdesc_k0(uint32_t tile_addr) { return make_sdesc(tile_addr, 16, 1024); }
+VBX_DEVINL uint64_t sdesc_mn0(uint32_t tile_addr) { return make_sdesc(tile_addr, kSubTileBytes, 1024); }
+__host__ __device__ constexpr uint64_t koff_k(int k) { return (uint64_t)(((k >> 2) * kSubTileBytes + (k & 3) * 32) >> 4); }
+__host__ __device__ constexpr uint64_t koff_mn(int k) { return (uint64_t)((k * 2048) >> 4); }
+
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
 VBX_DEVINL void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
