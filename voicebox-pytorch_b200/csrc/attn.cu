@@ -329,12 +329,12 @@ namespace bwd {
 constexpr int kStages = 3;  // Q/dO ring: the load of tile i+2 is issued as soon as the GEMMs of tile i-1 retire
 constexpr uint32_t kOffK = 0, kOffV = 16384, kOffQ = 32768, kOffdO = kOffQ + kStages * 16384,
                    kOffdST = kOffdO + kStages * 16384, kOffdQ = kOffdST + 32768, kOffBar = kOffdQ + 32768,
-                   kOffLse = kOffBar + 128, kOffDelta = kOffLse + 2 * kBM * 4;
-constexpr uint32_t kSmemBytes = kOffDelta + 2 * kBM * 4;  // 198,784 B: one CTA per SM (TMEM: all 512 columns)
-enum { KV_FULL = 0, QD_FULL = 1, QD_EMPTY = 4, ST_FULL = 7, ST_FREE = 8, DS_FULL = 9, DQ_FULL = 10, NUM_BARS = 11 };
+                   kOffStat = kOffBar + 128;  // per compute warp, double buffered: [8 warps][2][64 -lse | 64 delta] f32
+constexpr uint32_t kSmemBytes = kOffStat + 8 * 2 * 128 * 4;  // 204,928 B: one CTA per SM (TMEM: all 512 columns)
+enum { KV_FULL = 0, QD_FULL = 1, QD_EMPTY = 4, ST_FULL = 7, ST_FREE = 8, DS_FULL = 9, DQ_FULL = 10, DQ_FREE = 11, NUM_BARS = 12 };
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColST = 0, kColDPT = 128, kColDV = 256, kColDK = 320, kColDQ = 384, kColPT = 448;  // P^T: bf16 pairs
-constexpr int kThreads = 320;
+constexpr int kThreads = 448;  // warps 0-7 compute, 8 TMA producer, 9 MMA issuer, 10-13 dQ flush
 }  // namespace bwd
 
 // One CTA per (key tile, head, batch); loops over the query tiles.  Everything is computed TRANSPOSED (keys on the
@@ -342,8 +342,9 @@ constexpr int kThreads = 320;
 //   S^T = K Q^T, dP^T = V dO^T  ->  P^T = 2^(c S^T - lse), dS^T = P^T (dP^T - delta)
 //   dV += P^T dO,  dK += dS^T Q,  dQ_i = dS K  (fp32, scaled by `scale`, staged in shared memory and added into dq by
 //   ONE TMA reduce-add per 128x32 block -- per-lane red.global atomics cost ~8000 clk per tile, 6x the five GEMMs)
-// 10 warps: 0-7 compute (key row 32*(w%4)+lane, query-column half w/4: two threads per row -> 2 warps per SM
-// sub-partition), 8 TMA producer, 9 MMA issuer.  Software pipeline: the S^T/dP^T GEMMs of tile i+1 are issued BEFORE the
+// 14 warps: 0-7 compute (key row 32*(w%4)+lane, query-column half w/4: two threads per row -> 2 warps per SM
+// sub-partition), 8 TMA producer, 9 MMA issuer, 10-13 dQ flush (TMEM -> shared -> TMA reduce-add, off the compute warps'
+// critical path).  Software pipeline: the S^T/dP^T GEMMs of tile i+1 are issued BEFORE the
 // dV/dK/dQ GEMMs of tile i, and the compute warps keep P^T/dS^T of tile i+1 in registers until those GEMMs have finished
 // reading the shared-memory operand tiles -- so tensor pipe and exp/FMA pipes overlap instead of alternating.
 __global__ void __launch_bounds__(bwd::kThreads, 1)
@@ -356,8 +357,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + NUM_BARS * 8);
-  float* s_lse = reinterpret_cast<float*>(smem + kOffLse);      // [2][128]
-  float* s_delta = reinterpret_cast<float*>(smem + kOffDelta);  // [2][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * kBN, h = blockIdx.y, b = blockIdx.z;
@@ -375,6 +374,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
     mbar_init(&bars[ST_FREE], 256);
     mbar_init(&bars[DS_FULL], 256);
     mbar_init(&bars[DQ_FULL], 1);
+    mbar_init(&bars[DQ_FREE], 128);
     fence_barrier_init();
   }
   if (warp == 9) {
@@ -453,6 +453,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < kBM / 16; ++k)  // dK += dS^T Q
             umma_bf16(tmem_base + kColDK, dSk + koff_k(k), dQmn0 + so + koff_mn(k), idesc_kmn, (i > 0) || (k > 0));
+        }
+        __syncwarp();
+        mbar_wait(&bars[DQ_FREE], (i & 1) ^ 1);  // the flush warps have read dQ_{i-1} out of TMEM
+        tc_fence_after();
+        if (leader) {
 #pragma unroll
           for (int k = 0; k < kBN / 16; ++k)  // dQ_i = dS K    (A = dS^T read MN-major)
             umma_bf16(tmem_base + kColDQ, dSmn + koff_mn(k), dKmn + koff_mn(k), idesc_mnmn, k > 0);
@@ -463,68 +468,75 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         TRACE(0, i, 6);
       }
     }
-  } else {
-    const int half = warp >> 2;              // which 64 query columns of S^T / dP^T, which 32 columns of dQ / dV / dK
-    const int r = (warp & 3) * 32 + lane;    // TMEM lane: key row (S^T, dP^T, dV, dK) or query row (dQ)
+  } else if (warp >= 10) {
+    // ------------------------------------------------ dQ flush warps -----------------------------------------------
+    // dQ_i: TMEM -> registers -> shared -> TMA reduce-add into dq.  Warp w owns query rows [32(w%4), +32): a contiguous,
+    // 1024-byte aligned 4 KB slice of each [128 rows][32 fp32] SWIZZLE_128B staging block, reduced with its own 32x32 TMA
+    // ops (bulk groups are per thread: lane 0 waits for its previous group before the slice is overwritten).
+    const int r = (warp & 3) * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const int key = k0 + r;
-    float bias = 0.f;
-    if (key >= N) bias = -INFINITY;
-    else if (key_mask != nullptr && !key_mask[(int64_t)b * N + key]) bias = -FLT_MAX;
-
-    // dQ_i: TMEM -> registers -> shared -> TMA reduce-add into dq, with NO block-wide synchronisation: warp w owns rows
-    // [32(w%4), +32) of the [128 rows][32 fp32] SWIZZLE_128B block of its column half -- a contiguous, 1024-byte aligned
-    // 4 KB slice -- and issues its own 32x32 reduce (bulk groups are per thread: lane 0 waits for its previous one).
-    // stage: registers -> shared; issue: after the (single, shared) fence.proxy.async of the tile.
-    auto stage_dq = [&](int i) {
-      mbar_wait(&bars[DQ_FULL], i & 1);  // all GEMMs of tile i have retired: dQ_i is complete, P^T/dS^T smem is free
-      tc_fence_after();
-      if (lane == 0) tma_wait_group_read0();  // this warp's previous reduce has finished READING its slice
-      __syncwarp();
-      float v[32];
-      tmem_ld32(t_lane + kColDQ + half * 32, v);
-#pragma unroll
-      for (int qd = 0; qd < 8; ++qd) {
-        float4 o4 = make_float4(v[qd * 4] * scale, v[qd * 4 + 1] * scale, v[qd * 4 + 2] * scale, v[qd * 4 + 3] * scale);
-        *reinterpret_cast<float4*>(smem + kOffdQ + half * kTileBytes + r * 128 + ((qd ^ (r & 7)) << 4)) = o4;
-      }
-      tc_fence_before();
-    };
-    auto issue_dq = [&](int i) {  // caller has executed fence.proxy.async after stage_dq
-      __syncwarp();
-      if (lane == 0) {  // rows beyond N are clipped by the tensor map
-        tma_reduce_add_4d(&mdq, smem + kOffdQ + half * kTileBytes + (warp & 3) * 4096, half * 32, i * kBM + (warp & 3) * 32, h, b);
-        tma_commit_group();
-      }
-    };
-
-    float nlse = INFINITY, ndelta = 0.f;  // -lse / delta of this thread's query for the NEXT tile (register prefetch)
-    if (half == 0 && r < N) {
-      nlse = lse[bh * N + r];
-      ndelta = delta[bh * N + r];
-    }
-    const bool dead_row = bias != 0.f;  // padded or masked key: P^T row is exactly zero
-
     for (int i = 0; i < nq; ++i) {
-      const int st = i & 1, q0 = i * kBM;
-      if (half == 0) {
-        s_lse[st * kBM + r] = -nlse;  // stored NEGATED (folds into the FFMA); -inf -> p = 0 for padded queries
-        s_delta[st * kBM + r] = ndelta;
-        const int qn = q0 + kBM + r;  // issue the next tile's loads now: their latency hides behind this tile's math
-        nlse = INFINITY;
-        ndelta = 0.f;
-        if (i + 1 < nq && qn < N) {
-          nlse = lse[bh * N + qn];
-          ndelta = delta[bh * N + qn];
+      mbar_wait(&bars[DQ_FULL], i & 1);
+      tc_fence_after();
+      if (lane == 0) tma_wait_group_read0();
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float v[32];
+        tmem_ld32(t_lane + kColDQ + c * 32, v);
+        if (c == 1) {  // dQ_i is in registers: the MMA warp may start dQ_{i+1}
+          tc_fence_before();
+          mbar_arrive(&bars[DQ_FREE]);
+        }
+#pragma unroll
+        for (int qd = 0; qd < 8; ++qd) {
+          float4 o4 = make_float4(v[qd * 4] * scale, v[qd * 4 + 1] * scale, v[qd * 4 + 2] * scale, v[qd * 4 + 3] * scale);
+          *reinterpret_cast<float4*>(smem + kOffdQ + c * kTileBytes + r * 128 + ((qd ^ (r & 7)) << 4)) = o4;
         }
       }
-      if (threadIdx.x == 0) TRACE(1, i, 0);
-      named_bar_sync(1, 256);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {  // rows beyond N are clipped by the tensor map
+        tma_reduce_add_4d(&mdq, smem + kOffdQ + (warp & 3) * 4096, 0, i * kBM + (warp & 3) * 32, h, b);
+        tma_reduce_add_4d(&mdq, smem + kOffdQ + kTileBytes + (warp & 3) * 4096, 32, i * kBM + (warp & 3) * 32, h, b);
+        tma_commit_group();
+      }
+    }
+    if (lane == 0) tma_wait_group0();
+  } else {
+    // ------------------------------------------------ compute warps ------------------------------------------------
+    const int half = warp >> 2;              // which 64 query columns of S^T / dP^T, which 32 columns of dV / dK
+    const int r = (warp & 3) * 32 + lane;    // TMEM lane: key row
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const int key = k0 + r;
+    const bool dead_row = (key >= N) || (key_mask != nullptr && !key_mask[(int64_t)b * N + key]);  // P^T row is zero
+    // -lse / delta of this warp's 64 query columns live in a warp-private, double-buffered shared slice: lane l loads
+    // columns (2l, 2l+1) one tile ahead (register prefetch) and the warp only needs __syncwarp -- no block-wide barrier.
+    float* stat = reinterpret_cast<float*>(smem + kOffStat) + warp * 2 * 128;
+    auto load_stats = [&](int i, float2& nl, float2& dl) {
+      const int q = i * kBM + half * 64 + 2 * lane;
+      nl = make_float2(-INFINITY, -INFINITY);  // -lse = -inf -> p = 0 for padded queries
+      dl = make_float2(0.f, 0.f);
+      if (i < nq) {
+        if (q < N) nl.x = -lse[bh * N + q], dl.x = delta[bh * N + q];
+        if (q + 1 < N) nl.y = -lse[bh * N + q + 1], dl.y = delta[bh * N + q + 1];
+      }
+    };
+    float2 nl, dl;
+    load_stats(0, nl, dl);
+
+    for (int i = 0; i < nq; ++i) {
+      const int st = i & 1;
+      float* lrow_w = stat + st * 128;
+      *reinterpret_cast<float2*>(lrow_w + 2 * lane) = nl;
+      *reinterpret_cast<float2*>(lrow_w + 64 + 2 * lane) = dl;
+      load_stats(i + 1, nl, dl);  // next tile: latency hides behind this tile's math
+      __syncwarp();
       if (threadIdx.x == 0) TRACE(1, i, 1);
       mbar_wait(&bars[ST_FULL], i & 1);
       if (threadIdx.x == 0) TRACE(1, i, 2);
       tc_fence_after();
-      uint32_t pk[2][16], dsk[2][16];  // P^T / dS^T of this thread's 64 columns, packed bf16x2, held across the flush
+      uint32_t pk[2][16], dsk[2][16];  // P^T / dS^T of this thread's 64 columns, packed bf16x2, held until smem is free
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         float s[32], dp[32];
@@ -534,8 +546,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
           tc_fence_before();
           mbar_arrive(&bars[ST_FREE]);
         }
-        const float* lrow = s_lse + st * kBM + half * 64 + c * 32;    // -lse
-        const float* drow = s_delta + st * kBM + half * 64 + c * 32;
+        const float* lrow = lrow_w + c * 32;       // -lse
+        const float* drow = lrow_w + 64 + c * 32;  // delta
 #pragma unroll
         for (int x = 0; x < 32; x += 2) {
           const float p0 = ex2(fmaf(s[x], scale_log2, lrow[x]));
@@ -554,7 +566,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
           for (int x = 0; x < 16; ++x) pk[c][x] = dsk[c][x] = 0u;
       }
       if (threadIdx.x == 0) TRACE(1, i, 3);
-      if (i > 0) stage_dq(i - 1);  // waits for tile i-1's GEMMs: after this the P^T / dS^T shared tiles may be overwritten
+      if (i > 0) {  // tile i-1's GEMMs have retired: P^T (TMEM) and dS^T (shared) may be overwritten
+        mbar_wait(&bars[DQ_FULL], (i - 1) & 1);
+        tc_fence_after();
+      }
       if (threadIdx.x == 0) TRACE(1, i, 4);
       // P^T -> TMEM (A operand of the TS-mode dV GEMM: never touches shared memory); dS^T -> shared (K-major for dK, and
       // read MN-major for dQ)
@@ -572,16 +587,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
       }
       tmem_st_wait();
       tc_fence_before();
-      fence_proxy_async();  // ONE generic->async proxy fence per tile covers the dQ staging and the dS^T tile
+      fence_proxy_async();
       if (threadIdx.x == 0) TRACE(1, i, 5);
       mbar_arrive(&bars[DS_FULL]);
-      if (i > 0) issue_dq(i - 1);
       if (threadIdx.x == 0) TRACE(1, i, 6);
     }
-    stage_dq(nq - 1);
-    fence_proxy_async();
-    issue_dq(nq - 1);
-    if (lane == 0) tma_wait_group0();
+    mbar_wait(&bars[DQ_FULL], (nq - 1) & 1);
+    tc_fence_after();
     // all GEMMs have retired: write this thread's 32 columns of dV and dK for its key row.  The TMEM loads are
     // .sync.aligned (whole warp, converged); only the global stores are predicated on the key being real.
     {
