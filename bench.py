@@ -159,10 +159,14 @@ def main():
     ap.add_argument('--depth', type=int, default=DEPTH)
     ap.add_argument('--no-sample', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-only', action='store_true',
+                    help='for ncu launch lists only: allows --warmup < 3, skips the e2e / sampling / CPU legs; the printed number is NOT a bench value')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)
-    assert args.warmup >= 3 or args.steps == 0, 'timing rules: at least 3 warm-up steps'
+    assert args.warmup >= 3 or args.profile_only, 'timing rules: at least 3 warm-up steps'
+    if args.profile_only:
+        args.no_sample = args.no_cpu_baseline = True
 
     import torch.distributed as dist
     import voicebox_pytorch_b200 as vbx
@@ -252,9 +256,12 @@ def main():
     def e2e_step():
         x = x_host.to(dev, non_blocking=True)
         return train_step(x).item()
-    for _ in range(2):
-        e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    if args.profile_only:
+        ms_e2e = float('nan')
+    else:
+        for _ in range(2):
+            e2e_step()
+        ms_e2e = timed(e2e_step, args.steps)
 
     frames = B * N * world * args.steps
     value = frames / (ms_dev / 1e3)
@@ -329,7 +336,7 @@ def main():
                                 peak_mem_gib=round(peak_mem, 1)),
                     e2e=dict(value=e2e_value, unit='frames/s', ms_per_step=ms_e2e / args.steps,
                              h2d_bytes_per_step=x_host.numel() * 4, d2h_bytes_per_step=4),
-                    gpu_launches=launches, roofline=roofline, kernels=kernels, clocks=clocks, sample=sample, cpu_baseline=cpu)
+                    profile_only=bool(args.profile_only), gpu_launches=launches, roofline=roofline, kernels=kernels, clocks=clocks, sample=sample, cpu_baseline=cpu)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

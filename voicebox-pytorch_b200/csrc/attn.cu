@@ -329,12 +329,14 @@ namespace bwd {
 constexpr int kStages = 3;  // Q/dO ring: the load of tile i+2 is issued as soon as the GEMMs of tile i-1 retire
 constexpr uint32_t kOffK = 0, kOffV = 16384, kOffQ = 32768, kOffdO = kOffQ + kStages * 16384,
                    kOffdST = kOffdO + kStages * 16384, kOffdQ = kOffdST + 32768, kOffBar = kOffdQ + 32768,
-                   kOffStat = kOffBar + 128;  // per compute warp, double buffered: [8 warps][2][64 -lse | 64 delta] f32
-constexpr uint32_t kSmemBytes = kOffStat + 8 * 2 * 128 * 4;  // 204,928 B: one CTA per SM (TMEM: all 512 columns)
+                   kOffStat = kOffBar + 128;  // per compute warp, double buffered: [16 warps][2][32 -lse | 32 delta] f32
+constexpr int kComputeWarps = 16;           // 4 threads per key row: 32 query columns of S^T / dP^T each
+constexpr int kProducerWarp = 16, kMmaWarp = 17, kFlushWarp0 = 18;
+constexpr uint32_t kSmemBytes = kOffStat + kComputeWarps * 2 * 64 * 4;  // 204,928 B: one CTA per SM (TMEM: all 512 columns)
 enum { KV_FULL = 0, QD_FULL = 1, QD_EMPTY = 4, ST_FULL = 7, ST_FREE = 8, DS_FULL = 9, DQ_FULL = 10, DQ_FREE = 11, NUM_BARS = 12 };
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColST = 0, kColDPT = 128, kColDV = 256, kColDK = 320, kColDQ = 384, kColPT = 448;  // P^T: bf16 pairs
-constexpr int kThreads = 448;  // warps 0-7 compute, 8 TMA producer, 9 MMA issuer, 10-13 dQ flush
+constexpr int kThreads = 704;  // warps 0-15 compute, 16 TMA producer, 17 MMA issuer, 18-21 dQ flush
 }  // namespace bwd
 
 // One CTA per (key tile, head, batch); loops over the query tiles.  Everything is computed TRANSPOSED (keys on the
@@ -342,9 +344,9 @@ constexpr int kThreads = 448;  // warps 0-7 compute, 8 TMA producer, 9 MMA issue
 //   S^T = K Q^T, dP^T = V dO^T  ->  P^T = 2^(c S^T - lse), dS^T = P^T (dP^T - delta)
 //   dV += P^T dO,  dK += dS^T Q,  dQ_i = dS K  (fp32, scaled by `scale`, staged in shared memory and added into dq by
 //   ONE TMA reduce-add per 128x32 block -- per-lane red.global atomics cost ~8000 clk per tile, 6x the five GEMMs)
-// 14 warps: 0-7 compute (key row 32*(w%4)+lane, query-column half w/4: two threads per row -> 2 warps per SM
-// sub-partition), 8 TMA producer, 9 MMA issuer, 10-13 dQ flush (TMEM -> shared -> TMA reduce-add, off the compute warps'
-// critical path).  Software pipeline: the S^T/dP^T GEMMs of tile i+1 are issued BEFORE the
+// 22 warps: 0-15 compute (key row 32*(w%4)+lane, query-column quarter w/4: FOUR threads per row -> 4 warps per SM
+// sub-partition hide the ex2 / TMEM / shared-memory latencies of the exp phase), 16 TMA producer, 17 MMA issuer, 18-21 dQ
+// flush (TMEM -> shared -> TMA reduce-add, off the compute warps' critical path).  Software pipeline: the S^T/dP^T GEMMs of tile i+1 are issued BEFORE the
 // dV/dK/dQ GEMMs of tile i, and the compute warps keep P^T/dS^T of tile i+1 in registers until those GEMMs have finished
 // reading the shared-memory operand tiles -- so tensor pipe and exp/FMA pipes overlap instead of alternating.
 __global__ void __launch_bounds__(bwd::kThreads, 1)
@@ -371,13 +373,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
       mbar_init(&bars[QD_EMPTY + s_], 1);
     }
     mbar_init(&bars[ST_FULL], 1);
-    mbar_init(&bars[ST_FREE], 256);
-    mbar_init(&bars[DS_FULL], 256);
+    mbar_init(&bars[ST_FREE], kComputeWarps * 32);
+    mbar_init(&bars[DS_FULL], kComputeWarps * 32);
     mbar_init(&bars[DQ_FULL], 1);
     mbar_init(&bars[DQ_FREE], 128);
     fence_barrier_init();
   }
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
@@ -386,7 +388,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == kProducerWarp) {
     if (lane == 0) {
       mbar_arrive_expect_tx(&bars[KV_FULL], 2 * kTileBytes);
       tma_load_4d(smem + kOffK, &mk, &bars[KV_FULL], 0, k0, h, b);
@@ -404,7 +406,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         tma_load_4d(smem + kOffdO + st * kTileBytes, &mdo, &bars[QD_FULL + st], 0, i * kBM, h, b);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     // warp-uniform control flow, hoisted descriptors (see the forward kernel): only the leader lane issues MMAs / commits
     {
       constexpr uint32_t idesc_kk = make_idesc(128, 128, false, false);
@@ -468,7 +470,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         TRACE(0, i, 6);
       }
     }
-  } else if (warp >= 10) {
+  } else if (warp >= kFlushWarp0) {
     // ------------------------------------------------ dQ flush warps -----------------------------------------------
     // dQ_i: TMEM -> registers -> shared -> TMA reduce-add into dq.  Warp w owns query rows [32(w%4), +32): a contiguous,
     // 1024-byte aligned 4 KB slice of each [128 rows][32 fp32] SWIZZLE_128B staging block, reduced with its own 32x32 TMA
@@ -505,65 +507,59 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
     if (lane == 0) tma_wait_group0();
   } else {
     // ------------------------------------------------ compute warps ------------------------------------------------
-    const int half = warp >> 2;              // which 64 query columns of S^T / dP^T, which 32 columns of dV / dK
+    const int qr = warp >> 2;                // which 32 query columns of S^T / dP^T, which 16 columns of dV / dK
     const int r = (warp & 3) * 32 + lane;    // TMEM lane: key row
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const int key = k0 + r;
     const bool dead_row = (key >= N) || (key_mask != nullptr && !key_mask[(int64_t)b * N + key]);  // P^T row is zero
-    // -lse / delta of this warp's 64 query columns live in a warp-private, double-buffered shared slice: lane l loads
-    // columns (2l, 2l+1) one tile ahead (register prefetch) and the warp only needs __syncwarp -- no block-wide barrier.
-    float* stat = reinterpret_cast<float*>(smem + kOffStat) + warp * 2 * 128;
-    auto load_stats = [&](int i, float2& nl, float2& dl) {
-      const int q = i * kBM + half * 64 + 2 * lane;
-      nl = make_float2(-INFINITY, -INFINITY);  // -lse = -inf -> p = 0 for padded queries
-      dl = make_float2(0.f, 0.f);
-      if (i < nq) {
-        if (q < N) nl.x = -lse[bh * N + q], dl.x = delta[bh * N + q];
-        if (q + 1 < N) nl.y = -lse[bh * N + q + 1], dl.y = delta[bh * N + q + 1];
-      }
+    // -lse / delta of this warp's 32 query columns live in a warp-private, double-buffered shared slice: lane l loads
+    // column l one tile ahead (register prefetch) and the warp only needs __syncwarp -- no block-wide barrier.
+    float* stat = reinterpret_cast<float*>(smem + kOffStat) + warp * 2 * 64;
+    auto load_stats = [&](int i, float& nl, float& dl) {
+      const int q = i * kBM + qr * 32 + lane;
+      nl = -INFINITY;  // -lse = -inf -> p = 0 for padded queries
+      dl = 0.f;
+      if (i < nq && q < N) nl = -lse[bh * N + q], dl = delta[bh * N + q];
     };
-    float2 nl, dl;
+    float nl, dl;
     load_stats(0, nl, dl);
 
     for (int i = 0; i < nq; ++i) {
-      const int st = i & 1;
-      float* lrow_w = stat + st * 128;
-      *reinterpret_cast<float2*>(lrow_w + 2 * lane) = nl;
-      *reinterpret_cast<float2*>(lrow_w + 64 + 2 * lane) = dl;
+      float* lrow_w = stat + (i & 1) * 64;
+      lrow_w[lane] = nl;
+      lrow_w[32 + lane] = dl;
       load_stats(i + 1, nl, dl);  // next tile: latency hides behind this tile's math
       __syncwarp();
       if (threadIdx.x == 0) TRACE(1, i, 1);
       mbar_wait(&bars[ST_FULL], i & 1);
       if (threadIdx.x == 0) TRACE(1, i, 2);
       tc_fence_after();
-      uint32_t pk[2][16], dsk[2][16];  // P^T / dS^T of this thread's 64 columns, packed bf16x2, held until smem is free
+      uint32_t pk[16], dsk[16];  // P^T / dS^T of this thread's 32 columns, packed bf16x2, held until smem / TMEM are free
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        float s[32], dp[32];
-        tmem_ld32(t_lane + kColST + half * 64 + c * 32, s);
-        tmem_ld32(t_lane + kColDPT + half * 64 + c * 32, dp);
+        float s[16], dp[16];
+        tmem_ld16(t_lane + kColST + qr * 32 + c * 16, s);
+        tmem_ld16(t_lane + kColDPT + qr * 32 + c * 16, dp);
         if (c == 1) {
           tc_fence_before();
           mbar_arrive(&bars[ST_FREE]);
         }
-        const float* lrow = lrow_w + c * 32;       // -lse
-        const float* drow = lrow_w + 64 + c * 32;  // delta
+        const float* lrow = lrow_w + c * 16;       // -lse
+        const float* drow = lrow_w + 32 + c * 16;  // delta
 #pragma unroll
-        for (int x = 0; x < 32; x += 2) {
+        for (int x = 0; x < 16; x += 2) {
           const float p0 = ex2(fmaf(s[x], scale_log2, lrow[x]));
           const float p1 = ex2(fmaf(s[x + 1], scale_log2, lrow[x + 1]));
           const float d0 = p0 * (dp[x] - drow[x]);
           const float d1 = p1 * (dp[x + 1] - drow[x + 1]);
           __nv_bfloat162 pp = f2bf(p0, p1), dd = f2bf(d0, d1);
-          pk[c][x >> 1] = *reinterpret_cast<uint32_t*>(&pp);
-          dsk[c][x >> 1] = *reinterpret_cast<uint32_t*>(&dd);
+          pk[c * 8 + (x >> 1)] = *reinterpret_cast<uint32_t*>(&pp);
+          dsk[c * 8 + (x >> 1)] = *reinterpret_cast<uint32_t*>(&dd);
         }
       }
       if (dead_row) {  // rare (tail tile / masked keys): the whole row of P^T and dS^T is zero
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int x = 0; x < 16; ++x) pk[c][x] = dsk[c][x] = 0u;
+        for (int x = 0; x < 16; ++x) pk[x] = dsk[x] = 0u;
       }
       if (threadIdx.x == 0) TRACE(1, i, 3);
       if (i > 0) {  // tile i-1's GEMMs have retired: P^T (TMEM) and dS^T (shared) may be overwritten
@@ -572,18 +568,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
       }
       if (threadIdx.x == 0) TRACE(1, i, 4);
       // P^T -> TMEM (A operand of the TS-mode dV GEMM: never touches shared memory); dS^T -> shared (K-major for dK, and
-      // read MN-major for dQ)
-      tmem_st16(t_lane + kColPT + half * 32, pk[0]);
-      tmem_st16(t_lane + kColPT + half * 32 + 16, pk[1]);
+      // read MN-major for dQ).  This thread's 32 query columns = 4 16-byte chunks of 64-query sub-tile qr/2.
+      tmem_st16(t_lane + kColPT + qr * 16, pk);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-#pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
-          const int cc = c * 4 + qd;  // 16-byte chunk inside this half's 64-query sub-tile
-          const uint32_t off = half * kSubTileBytes + r * 128 + ((cc ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(smem + kOffdST + off) =
-              make_uint4(dsk[c][qd * 4], dsk[c][qd * 4 + 1], dsk[c][qd * 4 + 2], dsk[c][qd * 4 + 3]);
-        }
+      for (int qd = 0; qd < 4; ++qd) {
+        const int cc = (qr & 1) * 4 + qd;
+        const uint32_t off = (qr >> 1) * kSubTileBytes + r * 128 + ((cc ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(smem + kOffdST + off) = make_uint4(dsk[qd * 4], dsk[qd * 4 + 1], dsk[qd * 4 + 2], dsk[qd * 4 + 3]);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -594,30 +585,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
     }
     mbar_wait(&bars[DQ_FULL], (nq - 1) & 1);
     tc_fence_after();
-    // all GEMMs have retired: write this thread's 32 columns of dV and dK for its key row.  The TMEM loads are
+    // all GEMMs have retired: write this thread's 16 columns of dV and dK for its key row.  The TMEM loads are
     // .sync.aligned (whole warp, converged); only the global stores are predicated on the key being real.
     {
       const bool live = key < N;
-      uint16_t* dvp = dv + (int64_t)b * dv_bs + (int64_t)(live ? key : 0) * dv_ns + h * kDh + half * 32;
-      uint16_t* dkp = dk + (bh * N + (live ? key : 0)) * kDh + half * 32;
-      float v[32];
-      tmem_ld32(t_lane + kColDV + half * 32, v);
+      uint16_t* dvp = dv + (int64_t)b * dv_bs + (int64_t)(live ? key : 0) * dv_ns + h * kDh + qr * 16;
+      uint16_t* dkp = dk + (bh * N + (live ? key : 0)) * kDh + qr * 16;
+      float v[16];
+      tmem_ld16(t_lane + kColDV + qr * 16, v);
       if (live) {
-#pragma unroll
-        for (int x = 0; x < 32; x += 8) stg_16(dvp + x, pack8(&v[x]));
+        stg_16(dvp, pack8(&v[0]));
+        stg_16(dvp + 8, pack8(&v[8]));
       }
-      tmem_ld32(t_lane + kColDK + half * 32, v);
+      tmem_ld16(t_lane + kColDK + qr * 16, v);
 #pragma unroll
-      for (int x = 0; x < 32; ++x) v[x] *= scale;
+      for (int x = 0; x < 16; ++x) v[x] *= scale;
       if (live) {
-#pragma unroll
-        for (int x = 0; x < 32; x += 8) stg_16(dkp + x, pack8(&v[x]));
+        stg_16(dkp, pack8(&v[0]));
+        stg_16(dkp + 8, pack8(&v[8]));
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == bwd::kMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // =====================================================================================================================

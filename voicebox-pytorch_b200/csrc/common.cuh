@@ -32,13 +32,13 @@ VBX_DEVINL uint4 ldg_16(const void* p) {
   uint4 r;
   asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p)
-               : "memory");
+               : "l"(p));
   return r;
 }
 VBX_DEVINL void stg_16(void* p, uint4 v) {
-  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-               : "memory");
+  // no "memory" clobber: volatile asm statements stay ordered among themselves, while the compiler remains free to hoist
+  // independent plain loads (gamma/beta tables) above these streaming stores
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
 
 VBX_DEVINL void unpack8(uint4 u, float f[8]) {

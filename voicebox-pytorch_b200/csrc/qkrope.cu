@@ -219,7 +219,7 @@ extern "C" int vbx_qkrope_bwd(const uint16_t* qkv, const float* cosv, const floa
   VBX_REQUIRE(B > 0 && N > 0 && H > 0, VBX_E_SHAPE);
   VBX_REQUIRE(VBX_ALIGNED16(qkv) && VBX_ALIGNED16(dqh) && VBX_ALIGNED16(dkh) && VBX_ALIGNED16(dqkv), VBX_E_ALIGN);
   const int64_t nvec = B * N * 2 * H;
-  // 2 resident blocks per SM (122 registers): more blocks would only multiply the dgamma atomics (16 per thread)
+  // 2 resident blocks per SM (122 registers; forcing 3 spills and is slower): more blocks would only multiply the dgamma atomics
   qkrope_bwd_kernel<<<(unsigned)rope_grid(nvec, H, 2), 256, 0, (cudaStream_t)stream>>>(qkv, cosv, sinv, gq, gk, dqh, dkh, dqkv, dgq, dgk, B, N,
                                                                       (int)H);
   return VBX_LAUNCH_RC();
