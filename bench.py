@@ -189,7 +189,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        os.environ['NCCL_DEBUG'] = 'WARN'   # keep stdout to the single JSON line (NCCL_DEBUG=VERSION prints a banner there)
+        # keep stdout to the single JSON line: NCCL prints its version banner (NCCL_DEBUG >= VERSION) to stdout by default
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     peaks = load_peaks()
     B, N, D = args.batch, SEQ, DIM
