@@ -31,6 +31,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 DIM, DEPTH, HEADS, SEQ, REG = 1024, 24, 16, 1024, 16
+_REAL_STDOUT = sys.stdout
 METRIC = 'cfm_train_frames_per_sec'
 
 
@@ -118,7 +119,7 @@ def run_reference_arm(args):
                 config=dict(workload=f'VoiceBox dim{DIM} depth{DEPTH} heads{HEADS} seq{SEQ} CFM train step; CPU sample: batch 1, '
                                      f'{CPU_SAMPLE_DEPTH}/{DEPTH} layers timed and scaled (see cpu_baseline.sample)'),
                 cpu_baseline=base, e2e=dict(value=base['value'], unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -168,10 +169,19 @@ def main():
     ap.add_argument('--batch', type=int, default=64, help='batch per GPU (BASELINE configs[2]: 64)')
     ap.add_argument('--depth', type=int, default=DEPTH)
     ap.add_argument('--no-sample', action='store_true')
+    ap.add_argument('--allreduce', default=os.environ.get('VBX_ALLREDUCE', 'after'), choices=['overlap', 'after'],
+                    help='gradient exchange: ONE all-reduce of the flat bucket after backward (default; measured faster: NCCL CTAs '
+                         'otherwise take SMs from the 1-CTA/SM backward kernels), or chunked all-reduce overlapped with backward')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-only', action='store_true',
                     help='for ncu launch lists only: allows --warmup < 3, skips the e2e / sampling / CPU legs; the printed number is NOT a bench value')
     args = ap.parse_args()
+    # Only the JSON line may reach stdout: keep a private handle on the real stdout and point fd 1 at stderr, so banners printed
+    # by libraries (e.g. "NCCL version ...") cannot precede it.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     if args.impl == 'reference':
         return run_reference_arm(args)
     assert args.warmup >= 3 or args.profile_only, 'timing rules: at least 3 warm-up steps'
@@ -204,7 +214,7 @@ def main():
             if 'to_gamma.weight' in n_ or 'to_beta.weight' in n_:
                 p.normal_(0, 0.02, generator=g)
     w = vbx.ConditionalFlowMatcherWrapper(voicebox=vb).to(dev)
-    bucket = FlatGradBucket(w)
+    bucket = FlatGradBucket(w, overlap=(args.allreduce == 'overlap'))
     bucket.broadcast_parameters(w)
     n_params = sum(p.numel() for p in w.parameters() if p.requires_grad)
     opt = torch.optim.Adam([p for p in w.parameters() if p.requires_grad], lr=3e-4, betas=(0.9, 0.99), fused=True)
@@ -343,12 +353,12 @@ def main():
                     data='synthetic',
                     config=dict(workload=f'VoiceBox dim{D} depth{args.depth} heads{HEADS} seq{N} (+{REG} register tokens) '
                                          f'batch {B}/GPU, CFM loss fwd+bwd+allreduce+clip+Adam', global_batch=B * world,
-                                seq_len=N, parallelism=f'dp{world}', params=n_params, l2='inputs (268 MB/step) exceed the 126 MB L2',
+                                seq_len=N, parallelism=f'dp{world}', allreduce=args.allreduce, params=n_params, l2='inputs (268 MB/step) exceed the 126 MB L2',
                                 peak_mem_gib=round(peak_mem, 1)),
                     e2e=dict(value=e2e_value, unit='frames/s', ms_per_step=ms_e2e / args.steps,
                              h2d_bytes_per_step=x_host.numel() * 4, d2h_bytes_per_step=4),
                     profile_only=bool(args.profile_only), gpu_launches=launches, roofline=roofline, kernels=kernels, clocks=clocks, sample=sample, cpu_baseline=cpu)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -18,7 +18,8 @@ import torch.distributed as dist
 
 
 class FlatGradBucket:
-    def __init__(self, module, process_group=None, chunk_bytes=64 << 20):
+    def __init__(self, module, process_group=None, chunk_bytes=64 << 20, overlap=True):
+        self.overlap = overlap  # False: one all-reduce over the whole bucket in finish() (no SM sharing with the backward)
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.params = [p for p in reversed(list(module.parameters())) if p.requires_grad]
@@ -55,7 +56,7 @@ class FlatGradBucket:
 
     # ---- hooks ---------------------------------------------------------------------------------------------------
     def _hook(self, p):
-        if not self._sync or self.world == 1:
+        if not self._sync or self.world == 1 or not self.overlap:
             return
         c = self._chunk_of[id(p)]
         self._seen[c] += 1
@@ -82,6 +83,10 @@ class FlatGradBucket:
         """Call after backward of the last micro-step: flushes chunks whose parameters got no gradient, waits for the
         collectives (the current stream waits; no host sync with NCCL), and leaves the MEAN gradient in every .grad."""
         if self.world > 1 and self._sync:
+            if not self.overlap:
+                op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+                self._handles.append(dist.all_reduce(self.flat, op=op, group=self.group, async_op=True))
+                self._sent = [True] * len(self.chunks)
             for c in range(len(self.chunks)):
                 if not self._sent[c]:
                     self._launch(c)
