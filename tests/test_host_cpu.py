@@ -95,7 +95,7 @@ def test_no_cpu_fallback():
 
 
 # ---- world_size-2 gloo: flat gradient bucket -------------------------------------------------------------------------
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, overlap=True):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -105,7 +105,7 @@ def _worker(rank, world, port, out):
     model[3].weight.requires_grad_(True)
     unused = torch.nn.Linear(3, 3)  # never used by the loss (like duration_predictor inside the wrapper)
     model.add_module('unused', unused)
-    bucket = FlatGradBucket(model, chunk_bytes=256)  # tiny chunks -> several collectives
+    bucket = FlatGradBucket(model, chunk_bytes=256, overlap=overlap)  # tiny chunks -> several collectives when overlapped
     bucket.broadcast_parameters(model)
     assert len(bucket.chunks) > 1
     g = torch.Generator().manual_seed(100 + rank)
@@ -126,12 +126,14 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_flat_bucket_allreduce_gloo_world2():
+@pytest.mark.parametrize('overlap', [True, False])
+def test_flat_bucket_allreduce_gloo_world2(overlap):
+    """both exchange modes: chunked all-reduce from the grad hooks (overlap) and ONE all-reduce of the bucket in finish()"""
     world = 2
-    port = 29500 + (os.getpid() % 2000)
+    port = 29500 + (os.getpid() % 2000) + (7 if overlap else 0)
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, out, overlap), nprocs=world, join=True)
     n_unused = 3 * 3 + 3
     mean_local = (out[world + 0] + out[world + 1]) / 2
     for r in range(world):
