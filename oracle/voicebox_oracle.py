@@ -264,6 +264,16 @@ def voicebox_forward(sd, cfg, x, *, times, cond=None, cond_mask=None, target=Non
     return masked_mse(pred, target, loss_mask)
 
 
+def voicebox_forward_with_cond_scale(sd, cfg, x, *, cond_scale=1., **kw):
+    """vp.py:972-985 (classifier-free guidance): logits at cond_drop_prob = 0; if cond_scale != 1 a second pass at
+    cond_drop_prob = 1 (conditioning -> null_cond, token ids -> the null id) and null + (logits - null) * cond_scale."""
+    logits = voicebox_forward(sd, cfg, x, cond_drop_prob=0., **kw)
+    if cond_scale == 1.:
+        return logits
+    null = voicebox_forward(sd, cfg, x, cond_drop_prob=1., **kw)
+    return null + (logits - null) * cond_scale
+
+
 def cfm_interpolate(x0, x1, times, sigma=0.):
     """vp.py:1403-1410: w = (1-(1-s)t) x0 + t x1 ; flow = x1 - (1-s) x0."""
     t = times[:, None, None]

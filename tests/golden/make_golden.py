@@ -113,6 +113,31 @@ def voicebox_case(vp, name, *, dim, depth, heads, batch, seq, time_hidden_dim, s
     save(name, **arrays)
 
 
+def text_conditioned_case(vp, name, *, dim, depth, heads, batch, seq, n_tok, dim_emb, tok_len):
+    """Text-conditioned VoiceBox (vp.py:1058-1070: to_cond_emb gather + interpolate_1d to the latent length) in eval mode, and
+    classifier-free guidance through forward_with_cond_scale (vp.py:972-985; cond_drop_prob in {0,1} -> no RNG)."""
+    torch.manual_seed(0)
+    vb = vp.VoiceBox(dim=dim, depth=depth, dim_head=64, heads=heads, time_hidden_dim=dim, num_cond_tokens=n_tok,
+                     dim_cond_emb=dim_emb, condition_on_text=True)
+    perturb_adaptive(vb)
+    vb.eval()
+    sd = {k: v.detach().clone() for k, v in vb.state_dict().items()}
+    torch.manual_seed(6)
+    x = torch.randn(batch, seq, dim)
+    cond = torch.randn(batch, seq, dim)
+    times = torch.rand(batch)
+    ids = torch.randint(0, n_tok, (batch, tok_len))
+    cond_mask = torch.zeros(batch, seq, dtype=torch.bool)
+    cond_mask[:, seq // 3:] = True
+    with torch.no_grad():
+        pred = vb(x, times=times, cond_token_ids=ids, cond=cond, cond_mask=cond_mask, cond_drop_prob=0.)
+        guided = vb.forward_with_cond_scale(x, times=times, cond_token_ids=ids, cond=cond, cond_mask=cond_mask, cond_scale=1.3)
+    arrays = {f'sd/{k}': v for k, v in sd.items()}
+    arrays.update(dict(x=x, cond=cond, times=times, cond_token_ids=ids, cond_mask=cond_mask, pred=pred, guided=guided,
+                       cfg=np.array([dim, depth, heads, batch, seq, n_tok, dim_emb, tok_len])))
+    save(name, **arrays)
+
+
 def duration_case(vp, name, *, dim, depth, heads, batch, seq, n_tok, dim_emb):
     torch.manual_seed(0)
     dp = vp.DurationPredictor(num_phoneme_tokens=n_tok, dim_phoneme_emb=dim_emb, dim=dim, depth=depth, heads=heads)
@@ -172,6 +197,10 @@ if __name__ == '__main__':
         # no qk-norm => softmax scale 1/8: a well-conditioned fixture on which bf16 noise is NOT amplified (tight tolerances)
         voicebox_case(vp, 'voicebox_d128_l2_h4_n200_noqknorm', dim=128, depth=2, heads=4, batch=2, seq=200, time_hidden_dim=128,
                       qk_norm=False)
+        sys.exit(0)
+    if only == ['text']:
+        text_conditioned_case(vp, 'voicebox_text_d64_l2_h2_n120', dim=64, depth=2, heads=2, batch=2, seq=120, n_tok=20, dim_emb=32,
+                              tok_len=45)
         sys.exit(0)
     mask_kats(vp)
     # N'=216 = one full 128-key tile + an 88-key tail; heads*64 != dim; F = int(128*8/3) = 341 (not 8-aligned)

@@ -150,6 +150,28 @@ def test_duration_predictor_eval_vs_golden(vbx):
     assert maxerr(d, gold) <= max(1.5 * maxerr(db, gold), floor), (maxerr(d, gold), maxerr(db, gold))
 
 
+def test_text_conditioned_forward_and_cfg_vs_golden(vbx):
+    """Text-conditioned VoiceBox: to_cond_emb gather, interpolate_1d of the 45 token embeddings to 120 frames
+    (vp.py:1058-1070), and classifier-free guidance through forward_with_cond_scale (vp.py:972-985), public API, eval mode."""
+    a, sd = load_golden('voicebox_text_d64_l2_h2_n120', 'cuda')
+    dim, depth, heads, batch, seq, n_tok, dim_emb, tok_len = [int(v) for v in a['cfg']]
+    vb = vbx.VoiceBox(dim=dim, depth=depth, heads=heads, time_hidden_dim=dim, num_cond_tokens=n_tok, dim_cond_emb=dim_emb,
+                      condition_on_text=True).cuda()
+    vb.load_state_dict(sd, strict=True)
+    vb.eval()
+    cfg = dict(depth=depth, heads=heads, num_register_tokens=16, qk_norm=True, condition_on_text=True, num_cond_tokens=n_tok)
+    kw = dict(times=a['times'], cond=a['cond'], cond_mask=a['cond_mask'], cond_token_ids=a['cond_token_ids'])
+    with torch.no_grad():
+        pred = vb(a['x'], cond_drop_prob=0., **kw)
+        guided = vb.forward_with_cond_scale(a['x'], cond_scale=1.3, **kw)
+        pb = oracle_bf16(lambda: O.voicebox_forward(sd, cfg, a['x'], cond_drop_prob=0., **kw))
+        gb = oracle_bf16(lambda: O.voicebox_forward_with_cond_scale(sd, cfg, a['x'], cond_scale=1.3, **kw))
+    for mine, gold, bf in ((pred, a['pred'], pb), (guided, a['guided'], gb)):
+        assert mine.shape == gold.shape
+        floor = 2e-2 * float(gold.abs().max())
+        assert maxerr(mine, gold) <= max(1.5 * maxerr(bf, gold), floor), (maxerr(mine, gold), maxerr(bf, gold))
+
+
 def test_transformer_public_forward_plain_and_unet(vbx):
     """Transformer.forward (vp.py:412-479) stand-alone: plain RMSNorm, key mask, no registers; and the U-Net skip variant.
     Without qk-norm (softmax scale 1/8, well conditioned) the output must be within 3e-2 of the oracle's max; with qk-norm

@@ -63,6 +63,17 @@ def test_sampling_midpoint_euler(golden, name):
         close(s, a['sample_euler_steps4'])
 
 
+def test_text_conditioned_and_cfg(golden):
+    """to_cond_emb gather + interpolate_1d to the latent length (vp.py:1058-1070) and forward_with_cond_scale (vp.py:972-985)."""
+    a, sd = golden('voicebox_text_d64_l2_h2_n120')
+    dim, depth, heads, batch, seq, n_tok, dim_emb, tok_len = [int(v) for v in a['cfg']]
+    cfg = dict(depth=depth, heads=heads, num_register_tokens=16, qk_norm=True, condition_on_text=True, num_cond_tokens=n_tok)
+    kw = dict(times=a['times'], cond=a['cond'], cond_mask=a['cond_mask'], cond_token_ids=a['cond_token_ids'])
+    with torch.no_grad():
+        close(O.voicebox_forward(sd, cfg, a['x'], cond_drop_prob=0., **kw), a['pred'])
+        close(O.voicebox_forward_with_cond_scale(sd, cfg, a['x'], cond_scale=1.3, **kw), a['guided'])
+
+
 def test_duration_predictor_eval(golden):
     a, sd = golden('durpred_d128_l2_h2_n100')
     dim, depth, heads = [int(v) for v in a['cfg'][:3]]
