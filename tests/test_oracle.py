@@ -113,3 +113,27 @@ def test_fully_masked_keys_give_uniform_attention():
     q, k, v = torch.randn(3, 1, 2, 5, 8).unbind(0)
     o = O.attend(q, k, v, 1.0, torch.zeros(1, 5, dtype=torch.bool))
     assert torch.allclose(o, v.mean(-2, keepdim=True).expand_as(o), atol=1e-6)
+
+
+@pytest.mark.parametrize('method', ['euler', 'midpoint'])
+def test_fixed_grid_solver_known_answers(method):
+    """torchdiffeq is un-vendored (parity unpinned against the package itself), so the restated solver is pinned to the
+    PUBLISHED methods through closed forms on a non-uniform grid: explicit Euler and the explicit midpoint rule
+    (stage time t0 + dt/2, stage state y + f0 dt/2, full-step weight on the second evaluation)."""
+    t = torch.tensor([0., 0.1, 0.25, 0.45, 0.7, 1.0], dtype=torch.float64)
+    h = (t[1:] - t[:-1])
+    y0 = torch.tensor([1.0, -2.0], dtype=torch.float64)
+    # dy/dt = y: amplification factor per interval is (1+h) for Euler and (1+h+h^2/2) for midpoint
+    ys = O.odeint_fixed_grid(lambda tt, y: y, y0, t, method=method)
+    amp = (1 + h) if method == 'euler' else (1 + h + 0.5 * h * h)
+    want = torch.cat([torch.ones(1, dtype=torch.float64), torch.cumprod(amp, 0)])[:, None] * y0
+    assert ys.shape == (6, 2) and torch.allclose(ys, want, rtol=1e-13, atol=0)
+    # dy/dt = 3 t^2 pins the stage TIMES: Euler uses t0, midpoint uses t0 + h/2
+    ys = O.odeint_fixed_grid(lambda tt, y: 3 * tt * tt * torch.ones_like(y), torch.zeros(1, dtype=torch.float64), t, method=method)
+    ts = t[:-1] if method == 'euler' else t[:-1] + 0.5 * h
+    assert torch.allclose(ys[1:, 0], torch.cumsum(3 * ts * ts * h, 0), rtol=1e-13, atol=0)
+    # atol / rtol are accepted and ignored by fixed-grid solvers (the reference passes them: vp.py:1135-1139, 1295)
+    a = O.odeint_fixed_grid(lambda tt, y: y, y0, t, method=method, atol=1e-5, rtol=1e-5)
+    assert torch.equal(a, O.odeint_fixed_grid(lambda tt, y: y, y0, t, method=method))
+    with pytest.raises(NotImplementedError):
+        O.odeint_fixed_grid(lambda tt, y: y, y0, t, method='dopri5')
