@@ -776,10 +776,9 @@ extern "C" int vbx_attn_fwd(const uint16_t* q, const uint16_t* k, const uint16_t
   if ((rc = make_tmap_bf16_4d(&mq, q, N, H, B, kDh, N * kDh, H * N * kDh, kBM)) != VBX_OK) return rc;
   if ((rc = make_tmap_bf16_4d(&mk, k, N, H, B, kDh, N * kDh, H * N * kDh, kBN)) != VBX_OK) return rc;
   if ((rc = make_tmap_bf16_4d(&mv, v, N, H, B, v_ns, kDh, v_bs, kBN)) != VBX_OK) return rc;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd::kSmemBytes);
-  });
+  // per call, not once per process: the attribute is per device, and a host process may drive several GPUs
+  cudaError_t ce = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd::kSmemBytes);
+  if (ce != cudaSuccess) return (int)ce;
   dim3 grid((unsigned)((N + kBM - 1) / kBM), (unsigned)H, (unsigned)B);
   attn_fwd_kernel<<<grid, fwd::kThreads, fwd::kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, key_mask, scale * kLog2e, o, lse, (int)N,
                                                                        (int)H);
@@ -802,12 +801,10 @@ extern "C" int vbx_attn_bwd(const uint16_t* q, const uint16_t* k, const uint16_t
   if ((rc = make_tmap_bf16_4d(&mv, v, N, H, B, v_ns, kDh, v_bs, kBN)) != VBX_OK) return rc;
   if ((rc = make_tmap_bf16_4d(&mdo, dout, N, H, B, H * kDh, kDh, N * H * kDh, kBM)) != VBX_OK) return rc;
   if ((rc = make_tmap(&mdq, dq, kDh, N, H, B, kDh, N * kDh, H * N * kDh, 32, 4)) != VBX_OK) return rc;  // 32x32 fp32 boxes
+  cudaError_t ce = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd::kSmemBytes);
+  if (ce != cudaSuccess) return (int)ce;  // per call: the attribute is per device
   cudaStream_t s = (cudaStream_t)stream;
   attn_delta_kernel<<<grid_for(B * N * H, 32, 8), 256, 0, s>>>(o, dout, delta, B, N, (int)H);
-  static std::once_flag once;
-  std::call_once(once, [] {
-    cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd::kSmemBytes);
-  });
   dim3 grid((unsigned)((N + kBN - 1) / kBN), (unsigned)H, (unsigned)B);
   attn_bwd_kernel<<<grid, bwd::kThreads, bwd::kSmemBytes, s>>>(mq, mk, mv, mdo, mdq, key_mask, scale, scale * kLog2e, lse, delta, dk, dv,
                                                      dv_bs, dv_ns, (int)N, (int)H);
