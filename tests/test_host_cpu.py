@@ -141,3 +141,28 @@ def test_flat_bucket_allreduce_gloo_world2(overlap):
         assert torch.allclose(flat[:n_unused], torch.zeros(n_unused))       # unused params first (reverse order), zero
         assert torch.allclose(flat[n_unused:], mean_local, atol=1e-6)         # mean over ranks of accumulated grads
     assert torch.equal(out[0], out[1])
+
+
+def test_exp2_polynomial_constants_and_accuracy():
+    """csrc/attn.cu:ex2_poly (VBX_EXP_POLY experiment) -- the constants in the kernel source are the ones fitted by
+    tools/fit_exp2_poly.py, and its fp32 restatement stays within 1e-4 relative of exp2 over the softmax range (bf16 P
+    carries 2^-9), including positive arguments (backward: s - lse can exceed 0 by rounding) and the -125 clamp."""
+    import importlib.util
+    import re
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('fit_exp2_poly', os.path.join(root, 'tools', 'fit_exp2_poly.py'))
+    fp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fp)
+    src = open(os.path.join(root, 'voicebox-pytorch_b200', 'csrc', 'attn.cu')).read()
+    body = src[src.index('VBX_DEVINL float ex2_poly'):]
+    body = body[:body.index('}')]
+    consts = [float(v) for v in re.findall(r'(\d+\.\d+)f', body)]
+    assert consts[0] == 125.0 and consts[1] == consts[2] == 12582912.0
+    c3, c2, c1, c0 = consts[3:7]
+    assert (c0, c1, c2, c3) == fp.COEFFS
+    x = np.concatenate([np.linspace(-124.9, 3.0, 2_000_001), -np.abs(np.random.default_rng(1).normal(0, 4, 500_000))]).astype(np.float32)
+    got = fp.ex2_poly_fp32(x)
+    ref = np.exp2(x.astype(np.float64))
+    assert np.max(np.abs(got / ref - 1)) < 1e-4
+    assert fp.ex2_poly_fp32(np.array([-np.inf, -3e38], dtype=np.float32)).max() < 3e-38  # clamp: 2^-125, never NaN / garbage

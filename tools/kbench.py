@@ -51,11 +51,18 @@ def report(name, ms, gbytes=None, tflop=None):
 
 def main():
     B = int(os.environ.get('KB_B', 16))
+    only = os.environ.get('KB_ONLY', '')  # 'attn': only the attention / qk-rope lines (tools/attn_diagnose.sh)
+    torch.manual_seed(0)
+    if only != 'attn':
+        bench_elementwise(B)
+    bench_attention(B)
+
+
+def bench_elementwise(B):
     N, R, D, H = 1024, 16, 1024, 16
     Np = N + R
     T = B * Np
     dev = 'cuda'
-    torch.manual_seed(0)
     x = torch.randn(B, Np, D, device=dev)
     br = torch.randn(B, Np, D, device=dev).to(BF16)
     g = torch.rand(B, D, device=dev) + 0.5
@@ -113,6 +120,12 @@ def main():
     ms = timeit(lambda: ops.ode_axpy(y0, f, t, 0, 1, half=True, y_out=yo, emb=emb))
     report('ode_axpy (+emb)', ms, gbytes=B * N * D * 12 / 1e9)
 
+
+
+def bench_attention(B):
+    N, R, D, H = 1024, 16, 1024, 16
+    Np = N + R
+    dev = 'cuda'
     qkv = torch.randn(B, Np, 3 * H * 64, device=dev).to(BF16)
     inv_freq = 1.0 / (50000 ** (torch.arange(0, 64, 2, device=dev).float() / 64))
     pos = torch.cat((torch.full((R,), -10000, device=dev), torch.arange(N, device=dev))).float()

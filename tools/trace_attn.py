@@ -1,5 +1,5 @@
 """Development tool: per-tile clock64() timeline of CTA (1,0,0) of the attention kernels.  Needs the trace build:
-   nvcc ... -DVBX_TRACE -> voicebox-pytorch_b200/lib/libvbx_trace.so ; run with VBX_LIB=<that path>."""
+   VBX_EXP_DEFS=-DVBX_TRACE VBX_EXP_OUT=libvbx_trace.so voicebox-pytorch_b200/csrc/build_exp.sh ; run with VBX_LIB=<that path>."""
 import ctypes
 import os
 import sys
@@ -32,7 +32,7 @@ names = {0: ('bwd MMA', ['pre', 'QD_FULL', 'ST_FREE', 'S issued', 'preDS', 'DS_F
          1: ('bwd compute t0', ['top', 'bar1', 'ST_FULL', 'math done', 'flushed', 'stored', 'arrived']),
          2: ('bwd producer', ['QD_EMPTY ok']),
          3: ('fwd MMA', ['pre', 'K_FULL', 'S_FREE', 'S issued', 'V_FULL', 'P_FULL', 'PV issued']),
-         4: ('fwd softmax t0', ['top', 'S_FULL', 'pass1', 'bar', 'pass2', 'P arrived', 'O_FULL'])}
+         4: ('fwd softmax t0', ['top', 'S_FULL', 'pass1', 'bar', 'pass2', 'P arrived', 'O(j-1) accumulated (between bar and pass2)'])}
 for role, (nm, pts) in names.items():
     base = int(t[role][t[role] > 0].min()) if (t[role] > 0).any() else 0
     print(f'== {nm}  (clk relative to first stamp of this role; columns: {pts})')

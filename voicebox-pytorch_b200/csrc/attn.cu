@@ -21,6 +21,14 @@ constexpr int kBN = 128;  // keys per tile
 constexpr int kDh = 64;
 constexpr uint32_t kTileBytes = kBN * kDh * 2;  // 16 KB
 
+// EXPERIMENT, off in libvbx_sm100a.so (csrc/build_exp.sh builds lib/libvbx_exp.so with it on; select with VBX_LIB=...):
+// tail-aware tiles.  N' = N + 16 register tokens = 8*128 + 16, so the last key tile (forward) / last query tile (backward)
+// is 7/8 padding.  With the flag on, its S / S^T / dP^T GEMMs run with N = roundup(valid, 16) instead of 128, its P V / dV /
+// dK GEMMs with valid/16 K-steps instead of 8, and the softmax / exp code skips (warp-uniformly) chunks that are all padding.
+#ifndef VBX_EXP_TAIL
+#define VBX_EXP_TAIL 0
+#endif
+
 // ---- optional pipeline trace (built only with -DVBX_TRACE into lib/libvbx_trace.so; tools/trace_attn.py reads it) ----------
 #ifdef VBX_TRACE
 __device__ long long* g_trace = nullptr;
@@ -40,6 +48,26 @@ VBX_DEVINL float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// EXPERIMENT, off in libvbx_sm100a.so (VBX_EXP_DEFS=-DVBX_EXP_POLY=k csrc/build_exp.sh): both attention kernels are bound by
+// the 16 ex2/clk/SM of the MUFU pipe (1024 clk per 128x128 tile) while the FMA pipe idles.  With k in 1..4, k of every 4
+// consecutive exponentials are evaluated on the FMA/ALU pipes instead: round-to-nearest range reduction with the 1.5*2^23
+// magic constant, a degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, 50x below the bf16
+// rounding P gets anyway; fit + fp32 emulation in tools/fit_exp2_poly.py), exponent inserted with one shift-add.
+// Inputs are clamped at -125, so -inf gives 2^-125 (2.4e-38) instead of 0: only used where that is harmless (see call sites).
+#ifndef VBX_EXP_POLY
+#define VBX_EXP_POLY 0
+#endif
+VBX_DEVINL float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;       // low mantissa bits of t = round(x)
+  const float f = x - (t - 12582912.0f);  // in [-0.5, 0.5]
+  float p = fmaf(f, 0.0551716685295105f, 0.2426111251115799f);
+  p = fmaf(p, f, 0.6932609677314758f);
+  p = fmaf(p, f, 0.9999280571937561f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+// element i of an unrolled loop: MUFU or polynomial, decided at compile time
+#define VBX_EX2_AT(i, x) ((((i) & 3) < VBX_EXP_POLY) ? ex2_poly(x) : ex2(x))
 VBX_DEVINL float bf16_bits_to_float(uint16_t b) { return __uint_as_float((uint32_t)b << 16); }
 
 // =====================================================================================================================
@@ -140,10 +168,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
       const uint64_t dQ = sdesc_k0(smem_u32(smem + kOffQ));
       const uint64_t dK0 = sdesc_k0(smem_u32(smem + kOffK)), dV0 = sdesc_mn0(smem_u32(smem + kOffV));
       const bool leader = lane == 0;
+      const int n_tail = VBX_EXP_TAIL ? ((N - (nkv - 1) * kBN + 15) & ~15) : kBN;  // GEMM width of the last key tile
+      const uint32_t idesc_s_tail = make_idesc(kBM, n_tail, false, false);
       mbar_wait(&bars[Q_FULL], 0);
       auto issue_s = [&](int j) {  // S_j = Q K_j^T
         const int st = j & 1;
         const uint64_t dK = dK0 + (uint64_t)st * (kTileBytes >> 4);
+        const uint32_t idesc_sj = (VBX_EXP_TAIL && j == nkv - 1) ? idesc_s_tail : idesc_s;
         TRACE(3, j, 0);
         mbar_wait(&bars[K_FULL + st], (j >> 1) & 1);
         TRACE(3, j, 1);
@@ -152,7 +183,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         tc_fence_after();
         if (leader) {
 #pragma unroll
-          for (int k = 0; k < kDh / 16; ++k) umma_bf16(tmem_base, dQ + koff_k(k), dK + koff_k(k), idesc_s, k > 0);
+          for (int k = 0; k < kDh / 16; ++k) umma_bf16(tmem_base, dQ + koff_k(k), dK + koff_k(k), idesc_sj, k > 0);
           umma_commit(&bars[S_FULL]);
           umma_commit(&bars[K_EMPTY + st]);
         }
@@ -174,7 +205,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         if (leader) {
 #pragma unroll
           for (int k = 0; k < kBN / 16; ++k)  // A = P from TMEM: 8 columns (16 keys) per K-step
-            umma_bf16_ts(tmem_base + kColO, tmem_base + kColP + k * 8, dV + koff_mn(k), idesc_o, k > 0);
+            if (!VBX_EXP_TAIL || j < nkv - 1 || k * 16 < n_tail)
+              umma_bf16_ts(tmem_base + kColO, tmem_base + kColP + k * 8, dV + koff_mn(k), idesc_o, k > 0);
           umma_commit(&bars[O_FULL]);
           umma_commit(&bars[V_EMPTY + st]);
         }
@@ -213,8 +245,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
       tc_fence_after();
       // pass 1: partial max over this thread's 64 columns (scaled, masked logits; log2 domain)
       float mx = -FLT_MAX;
+      const int valid_cols = N - k0;  // >= 128 except in the tail tile
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
+        if (VBX_EXP_TAIL && half * 64 + c * 32 >= valid_cols) continue;  // warp-uniform: every key of this chunk is padding
         float s[32];
         tmem_ld32(t_lane + half * 64 + c * 32, s);
         if (masked_tile) {
@@ -246,11 +280,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         tc_fence_before();
       }
       alpha_prev = alpha;
+      if (threadIdx.x == 0) TRACE(4, j, 6);
       // pass 2: p = 2^(t - m), partial row sum, P -> TMEM (bf16 pairs: column kColP + key/2 of this row's lane)
       float rowsum = 0.f;
       const float neg_m = -m;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
+        if (VBX_EXP_TAIL && half * 64 + c * 32 >= valid_cols) {
+          // warp-uniform: all-padding chunk.  Its P columns belong to K-steps >= n_tail/16 that the P V GEMM does not issue,
+          // so nothing is loaded, computed or stored; only the S hand-off still has to happen.
+          if (c == 1) {
+            tc_fence_before();
+            mbar_arrive(&bars[S_FREE]);
+          }
+          continue;
+        }
         float s[32];
         tmem_ld32(t_lane + half * 64 + c * 32, s);
         if (c == 1) {  // this thread's part of S is in registers: release it to the MMA warp
@@ -259,10 +303,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         }
         if (masked_tile) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) s[i] = ex2(fmaf(s[i], scale_log2, bias[c * 32 + i]) + neg_m);
+          for (int i = 0; i < 32; ++i) {
+            const float bb = bias[c * 32 + i];
+            float t = fmaf(s[i], scale_log2, bb);
+            // S columns >= n_tail of the tail tile were not written by the narrowed GEMM: whatever bits they hold must not
+            // reach the row sum (NaN + -inf = NaN), so non-existent keys are selected, not added, to -inf
+            if (VBX_EXP_TAIL) t = (bb == -INFINITY) ? -INFINITY : t;
+            s[i] = ex2(t + neg_m);
+          }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) s[i] = ex2(fmaf(s[i], scale_log2, neg_m));
+          for (int i = 0; i < 32; ++i) s[i] = VBX_EX2_AT(i, fmaf(s[i], scale_log2, neg_m));  // every key exists: no -inf here
         }
         float r4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -437,8 +488,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
       const uint64_t dQk0 = sdesc_k0(smem_u32(smem + kOffQ)), dQmn0 = sdesc_mn0(smem_u32(smem + kOffQ));
       const uint64_t dOk0 = sdesc_k0(smem_u32(smem + kOffdO)), dOmn0 = sdesc_mn0(smem_u32(smem + kOffdO));
       const uint64_t dSk = sdesc_k0(smem_u32(smem + kOffdST)), dSmn = sdesc_mn0(smem_u32(smem + kOffdST));
+      const int n_qt = VBX_EXP_TAIL ? ((N - (nq - 1) * kBM + 15) & ~15) : kBM;  // GEMM width of the last query tile
+      const uint32_t idesc_kk_tail = make_idesc(128, n_qt, false, false);
       auto issue_s = [&](int i) {  // S^T = K Q_i^T, dP^T = V dO_i^T
         const uint64_t so = (uint64_t)(i % kStages) * (kTileBytes >> 4);
+        const uint32_t idesc_i = (VBX_EXP_TAIL && i == nq - 1) ? idesc_kk_tail : idesc_kk;
         TRACE(0, i, 0);
         mbar_wait(&bars[QD_FULL + i % kStages], (i / kStages) & 1);
         TRACE(0, i, 1);
@@ -448,10 +502,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         if (leader) {
 #pragma unroll
           for (int k = 0; k < kDh / 16; ++k)
-            umma_bf16(tmem_base + kColST, dKk + koff_k(k), dQk0 + so + koff_k(k), idesc_kk, k > 0);
+            umma_bf16(tmem_base + kColST, dKk + koff_k(k), dQk0 + so + koff_k(k), idesc_i, k > 0);
 #pragma unroll
           for (int k = 0; k < kDh / 16; ++k)
-            umma_bf16(tmem_base + kColDPT, dVk + koff_k(k), dOk0 + so + koff_k(k), idesc_kk, k > 0);
+            umma_bf16(tmem_base + kColDPT, dVk + koff_k(k), dOk0 + so + koff_k(k), idesc_i, k > 0);
           umma_commit(&bars[ST_FULL]);
         }
         __syncwarp();
@@ -470,10 +524,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         if (leader) {
 #pragma unroll
           for (int k = 0; k < kBM / 16; ++k)  // dV += P^T dO   (TS mode: P^T read from TMEM, only dO from shared memory)
-            umma_bf16_ts(tmem_base + kColDV, tmem_base + kColPT + k * 8, dOmn0 + so + koff_mn(k), idesc_kmn, (i > 0) || (k > 0));
+            if (!VBX_EXP_TAIL || i < nq - 1 || k * 16 < n_qt)
+              umma_bf16_ts(tmem_base + kColDV, tmem_base + kColPT + k * 8, dOmn0 + so + koff_mn(k), idesc_kmn, (i > 0) || (k > 0));
 #pragma unroll
           for (int k = 0; k < kBM / 16; ++k)  // dK += dS^T Q
-            umma_bf16(tmem_base + kColDK, dSk + koff_k(k), dQmn0 + so + koff_mn(k), idesc_kmn, (i > 0) || (k > 0));
+            if (!VBX_EXP_TAIL || i < nq - 1 || k * 16 < n_qt)
+              umma_bf16(tmem_base + kColDK, dSk + koff_k(k), dQmn0 + so + koff_mn(k), idesc_kmn, (i > 0) || (k > 0));
         }
         __syncwarp();
         mbar_wait(&bars[DQ_FREE], (i & 1) ^ 1);  // the flush warps have read dQ_{i-1} out of TMEM
@@ -531,6 +587,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const int key = k0 + r;
     const bool dead_row = (key >= N) || (key_mask != nullptr && !key_mask[(int64_t)b * N + key]);  // P^T row is zero
+    const bool warp_dead = VBX_EXP_TAIL && (k0 + (warp & 3) * 32) >= N;  // all 32 key rows of this warp are padding
     // -lse / delta of this warp's 32 query columns live in a warp-private, double-buffered shared slice: lane l loads
     // column l one tile ahead (register prefetch) and the warp only needs __syncwarp -- no block-wide barrier.
     float* stat = reinterpret_cast<float*>(smem + kOffStat) + warp * 2 * 64;
@@ -554,8 +611,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
       if (threadIdx.x == 0) TRACE(1, i, 2);
       tc_fence_after();
       uint32_t pk[16], dsk[16];  // P^T / dS^T of this thread's 32 columns, packed bf16x2, held until smem / TMEM are free
+      const int valid_q = N - i * kBM;  // >= 128 except in the tail query tile
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
+        if (VBX_EXP_TAIL && (qr * 32 + c * 16 >= valid_q || warp_dead)) {
+          // warp-uniform: every query of this 16-column chunk (columns the narrowed GEMMs did not even write), or every key
+          // row of this warp, is padding: exact zeros without touching TMEM or the exp unit
+          if (c == 1) {
+            tc_fence_before();
+            mbar_arrive(&bars[ST_FREE]);
+          }
+#pragma unroll
+          for (int x = 0; x < 8; ++x) pk[c * 8 + x] = dsk[c * 8 + x] = 0u;
+          continue;
+        }
         float s[16], dp[16];
         tmem_ld16(t_lane + kColST + qr * 32 + c * 16, s);
         tmem_ld16(t_lane + kColDPT + qr * 32 + c * 16, dp);
@@ -567,8 +636,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         const float* drow = lrow_w + 32 + c * 16;  // delta
 #pragma unroll
         for (int x = 0; x < 16; x += 2) {
-          const float p0 = ex2(fmaf(s[x], scale_log2, lrow[x]));
-          const float p1 = ex2(fmaf(s[x + 1], scale_log2, lrow[x + 1]));
+          // padded queries (-lse = -inf) may come out as 2^-125 instead of 0 from the polynomial: they only ever multiply
+          // zero-filled dO / Q rows and clipped dQ rows
+          const float p0 = VBX_EX2_AT(x, fmaf(s[x], scale_log2, lrow[x]));
+          const float p1 = VBX_EX2_AT(x + 1, fmaf(s[x + 1], scale_log2, lrow[x + 1]));
           const float d0 = p0 * (dp[x] - drow[x]);
           const float d1 = p1 * (dp[x + 1] - drow[x + 1]);
           __nv_bfloat162 pp = f2bf(p0, p1), dd = f2bf(d0, d1);
