@@ -4,6 +4,7 @@ Tolerances (stated per test): the kernels compute in fp32 and round ONCE to bf16
 same bf16-rounded inputs the expected error is one bf16 ulp (2^-8 relative) of the output magnitude; reductions accumulated
 with fp32 atomics are compared at 2e-3 relative to the result's max.  Index/mask semantics are exact."""
 import math
+import os
 
 import pytest
 import torch
@@ -212,7 +213,16 @@ def _attn_reference(qkv, H, gq, gk, pos, inv_freq, scale, key_mask):
     return o.transpose(1, 2).reshape(B, N, H * 64), q, k
 
 
-@pytest.mark.parametrize('B,H,N,R,qk_norm,masked', [
+# extra tail geometries for the tail-tile experiment (tools/attn_diagnose.sh sets VBX_EXTRA_GEOM=1); they join the default
+# list once they have been seen green on a B200
+_EXTRA_ATTN_GEOM = [
+    (1, 2, 130, 0, False, False),      # 1 full tile + a 2-key tail (narrowed GEMM N = 16, 14 padded columns inside it)
+    (1, 2, 255, 0, True, False),       # 127-key tail: narrowed width rounds back up to 128
+    (2, 2, 161, 0, False, True),       # 33-key tail + key-padding mask: N = 48, stale columns inside a loaded chunk
+] if os.environ.get('VBX_EXTRA_GEOM') else []
+
+
+@pytest.mark.parametrize('B,H,N,R,qk_norm,masked', _EXTRA_ATTN_GEOM + [
     (2, 2, 80, 16, True, False),       # single partial tile
     (2, 4, 216, 16, True, False),      # 1 full tile + 88-key tail (golden geometry)
     (1, 2, 128, 0, False, False),      # exactly one tile, no qk-norm (scale 1/8)
