@@ -166,3 +166,25 @@ def test_exp2_polynomial_constants_and_accuracy():
     ref = np.exp2(x.astype(np.float64))
     assert np.max(np.abs(got / ref - 1)) < 1e-4
     assert fp.ex2_poly_fp32(np.array([-np.inf, -3e38], dtype=np.float32)).max() < 3e-38  # clamp: 2^-125, never NaN / garbage
+
+
+def test_bf16_cast_cache_is_pinned_to_the_tensor_object():
+    """ops.cast_bf16 caches the bf16 copy of a frozen parameter per (object, version, data_ptr).  id() values, device
+    addresses and version counters are all reused once a model is freed, so an entry must never be served to another tensor
+    object, and an in-place update must invalidate it."""
+    import torch
+    from voicebox_pytorch_b200 import ops
+    ops.clear_cast_cache()
+    p = torch.nn.Parameter(torch.randn(8, 8))
+    with torch.no_grad():
+        a = ops.cast_bf16(p)
+        assert ops.cast_bf16(p) is a                       # hit
+        p.add_(1.0)
+        b = ops.cast_bf16(p)
+        assert b is not a and torch.equal(b, p.detach().to(torch.bfloat16))   # version bump -> miss
+        q = torch.nn.Parameter(torch.zeros(8, 8))
+        # forge the collision a freed-and-rebuilt model produces: q's key, p's (live) entry with q's version and address
+        ops._cast_cache[(id(q), '')] = (ops._cast_cache[(id(p), '')][0], q._version, q.data_ptr(), b)
+        assert torch.equal(ops.cast_bf16(q).float(), torch.zeros(8, 8))
+    assert ops.cast_bf16(p).requires_grad                  # grad mode: differentiable cast, never the cache
+    ops.clear_cast_cache()

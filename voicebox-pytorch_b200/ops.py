@@ -3,6 +3,8 @@
 Every op here runs hand-written sm_100a CUDA through `_lib.call`; GEMMs (`linear`) are plain library GEMMs through
 torch (cuBLASLt) on bf16 operands, exactly where the reference's autocast would run them.  Nothing falls back to CPU.
 """
+import weakref
+
 import torch
 import torch.nn.functional as F
 
@@ -25,7 +27,7 @@ _cast_cache = {}
 
 def cast_bf16(p, tag='', transform=None):
     """bf16 copy of parameter `p` (optionally through `transform`, e.g. the GEGLU zero-padding).  Differentiable when grad
-    is enabled; cached on (id, version, data_ptr) otherwise."""
+    is enabled; cached per tensor object (weakly referenced) and (version, data_ptr) otherwise."""
     if p is None:
         return None
     if torch.is_grad_enabled() and p.requires_grad:
@@ -33,12 +35,17 @@ def cast_bf16(p, tag='', transform=None):
         return transform(q) if transform is not None else q
     key = (id(p), tag)
     hit = _cast_cache.get(key)
-    if hit is not None and hit[0] == p._version and hit[1] == p.data_ptr():
-        return hit[2]
+    # the weak reference pins the entry to THIS tensor object: id() values (and, through the caching allocator, device
+    # addresses and version counters) are reused once a model is freed and another one is built
+    if hit is not None and hit[0]() is p and hit[1] == p._version and hit[2] == p.data_ptr():
+        return hit[3]
     with torch.no_grad():
         q = p.detach().to(BF16)
         q = transform(q) if transform is not None else q
-    _cast_cache[key] = (p._version, p.data_ptr(), q)
+    if len(_cast_cache) > 4096:  # entries of freed models are only dropped here
+        for k in [k for k, v in _cast_cache.items() if v[0]() is None]:
+            del _cast_cache[k]
+    _cast_cache[key] = (weakref.ref(p), p._version, p.data_ptr(), q)
     return q
 
 
