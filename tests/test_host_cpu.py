@@ -188,3 +188,50 @@ def test_bf16_cast_cache_is_pinned_to_the_tensor_object():
         assert torch.equal(ops.cast_bf16(q).float(), torch.zeros(8, 8))
     assert ops.cast_bf16(p).requires_grad                  # grad mode: differentiable cast, never the cache
     ops.clear_cast_cache()
+
+
+def test_batched_gamma_beta_matches_per_norm_linears():
+    """ops.batched_affine (the VBX_BATCHED_GB experiment: all adaptive norms' gamma/beta from one batched GEMM) against
+    the per-norm path it replaces (AdaptiveRMSNorm.gamma_beta -> ops.linear): same bf16 rounding points, so values agree to
+    a bf16 ulp and every parameter / input gradient to bf16 accumulation noise.  Pure torch: runs on CPU."""
+    import torch
+    from voicebox_pytorch_b200 import ops
+    from voicebox_pytorch_b200.modules import AdaptiveRMSNorm
+    torch.manual_seed(0)
+    B, C, D, K = 5, 48, 32, 3
+    norms = [AdaptiveRMSNorm(D, cond_dim=C) for _ in range(K)]
+    for n in norms:
+        for p in n.parameters():
+            torch.nn.init.normal_(p, 0, 0.3)
+    cond = torch.randn(B, C)
+
+    def run(batched):
+        for n in norms:
+            n.zero_grad()
+        c = cond.clone().requires_grad_()
+        cb = c.to(torch.bfloat16)
+        if batched:
+            gbs = ops.batched_affine(cb, [w for n in norms for w in (n.to_gamma.weight, n.to_beta.weight)],
+                                     [b for n in norms for b in (n.to_gamma.bias, n.to_beta.bias)])
+            outs = [t for t in gbs]
+        else:
+            outs = [t for n in norms for t in n.gamma_beta(cb)]
+        assert all(t.dtype == torch.float32 and t.is_contiguous() and t.shape == (B, D) for t in outs)
+        torch.manual_seed(1)
+        loss = sum((t * torch.randn_like(t)).sum() for t in outs)
+        loss.backward()
+        grads = [p.grad.clone() for n in norms for p in n.parameters()]
+        return [t.detach() for t in outs], grads, c.grad.clone()
+
+    o1, g1, c1 = run(False)
+    o2, g2, c2 = run(True)
+    for a, b in zip(o1, o2):
+        assert torch.allclose(a, b, rtol=2 ** -7, atol=1e-3)
+    for a, b in zip(g1, g2):
+        assert a.shape == b.shape and b.dtype == torch.float32
+        assert (a - b).abs().max() <= 2e-2 * a.abs().max() + 1e-6
+    assert (c1 - c2).abs().max() <= 2e-2 * c1.abs().max()
+    with torch.no_grad():  # sampling path: no autograd node, same values
+        gbs = ops.batched_affine(cond.to(torch.bfloat16), [w for n in norms for w in (n.to_gamma.weight, n.to_beta.weight)],
+                                 [b for n in norms for b in (n.to_gamma.bias, n.to_beta.bias)])
+        assert all(torch.equal(a, b) for a, b in zip(gbs, o2)) and not gbs[0].requires_grad

@@ -9,6 +9,7 @@ the layout the reference itself reaches under `torch.autocast(bfloat16)` (SURVEY
 Not implemented (raise at construction, no silent fallback): GateLoop layers, torchode, dropout p > 0.
 """
 import math
+import os
 from pathlib import Path
 from random import random
 
@@ -20,6 +21,8 @@ from . import ops
 from .ode import odeint_fixed, METHODS
 
 BF16 = torch.bfloat16
+# EXPERIMENT (off by default until timed on a B200): batch the adaptive norms' gamma/beta projections, see ops.batched_affine
+BATCHED_GAMMA_BETA = os.environ.get('VBX_BATCHED_GB', '0') == '1'
 
 
 def exists(v):
@@ -339,7 +342,18 @@ def transformer_trunk(self, x, mask, cond, n_out):
     if exists(mask):
         mask = mask.contiguous()
 
+    batched = {}
+    if BATCHED_GAMMA_BETA and exists(cond_bf16):
+        # every adaptive norm's (gamma, beta) from ONE batched GEMM over the time embedding instead of 2 tiny GEMMs per norm
+        norms = [n for layer in self.layers for n in (layer[2], layer[4]) if hasattr(n, 'to_gamma')]
+        if norms:
+            gbs = ops.batched_affine(cond_bf16, [w for n in norms for w in (n.to_gamma.weight, n.to_beta.weight)],
+                                     [b for n in norms for b in (n.to_gamma.bias, n.to_beta.bias)])
+            batched = {id(n): (gbs[2 * i], gbs[2 * i + 1]) for i, n in enumerate(norms)}
+
     def gb(norm):
+        if id(norm) in batched:
+            return batched[id(norm)]
         if hasattr(norm, 'to_gamma'):  # AdaptiveRMSNorm: gamma/beta from the time embedding (vp.py:273)
             return AdaptiveRMSNorm.gamma_beta(norm, cond_bf16)
         return norm.gamma, None

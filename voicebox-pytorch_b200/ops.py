@@ -51,6 +51,57 @@ def cast_bf16(p, tag='', transform=None):
 
 def clear_cast_cache():
     _cast_cache.clear()
+    _stack_cache.clear()
+
+
+class _StackCastBf16(torch.autograd.Function):
+    """bf16 stack [K, *shape] of K same-shape fp32 parameters with ONE multi-tensor cast (instead of K casts + a cat);
+    the backward hands every parameter the fp32, contiguous slice of the stacked gradient."""
+
+    @staticmethod
+    def forward(ctx, *ps):
+        out = torch.empty((len(ps),) + tuple(ps[0].shape), device=ps[0].device, dtype=BF16)
+        torch._foreach_copy_(list(out.unbind(0)), [p.detach() for p in ps])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return tuple(g.to(torch.float32, memory_format=torch.contiguous_format).unbind(0))
+
+
+_stack_cache = {}
+
+
+def stack_cast_bf16(ps, tag=''):
+    """Differentiable when grad is enabled; otherwise (sampling: constant weights, 2 evaluations per solver step) cached on
+    the parameter objects and their (version, data_ptr) like `cast_bf16`."""
+    ps = list(ps)
+    if torch.is_grad_enabled() and any(p.requires_grad for p in ps):
+        return _StackCastBf16.apply(*ps)
+    key = (tag, id(ps[0]), len(ps))
+    sig = tuple((p._version, p.data_ptr()) for p in ps)
+    hit = _stack_cache.get(key)
+    if hit is not None and hit[0]() is ps[0] and hit[1] == sig:
+        return hit[2]
+    with torch.no_grad():
+        q = _StackCastBf16.forward(None, *ps)
+    _stack_cache[key] = (weakref.ref(ps[0]), sig, q)
+    return q
+
+
+def batched_affine(cond_bf16, weights, biases):
+    """y[k] = cond @ weights[k]^T + biases[k] for K same-shape Linear layers as ONE batched library GEMM (bf16 operands,
+    fp32 accumulate, bf16 output -- the same rounding points as K separate `linear` calls).  cond bf16 [B, C];
+    weights K x f32 [D, C]; biases K x f32 [D].  Returns a tuple of K contiguous f32 [B, D] tensors (views of one buffer).
+
+    The 48 adaptive norms of the Voicebox trunk need 96 such [B x C] x [C x D] products per forward (vp.py:273-274): done
+    one by one they cost ~1100 tiny launches per training step (casts, GEMMs, bias reductions, gradient casts)."""
+    K = len(weights)
+    W = stack_cast_bf16(weights, 'w')            # [K, D, C]
+    bvec = stack_cast_bf16(biases, 'b')          # [K, D]
+    B, C = cond_bf16.shape
+    out = torch.baddbmm(bvec[:, None, :], cond_bf16.unsqueeze(0).expand(K, B, C), W.transpose(1, 2))  # [K, B, D] bf16
+    return out.float().unbind(0)
 
 
 def linear(x, weight, bias=None, tag=''):
