@@ -169,6 +169,9 @@ def main():
     ap.add_argument('--batch', type=int, default=64, help='batch per GPU (BASELINE configs[2]: 64)')
     ap.add_argument('--depth', type=int, default=DEPTH)
     ap.add_argument('--no-sample', action='store_true')
+    ap.add_argument('--optimizer', default=os.environ.get('VBX_OPTIMIZER', 'torch'), choices=['torch', 'flat'],
+                    help="'torch': torch.optim.Adam(fused=True) with the clip folded into its grad_scale; 'flat': "
+                         "voicebox_pytorch_b200.FlatAdam = one vbx_adam_step launch over the flat buffers (experiment)")
     ap.add_argument('--allreduce', default=os.environ.get('VBX_ALLREDUCE', 'after'), choices=['overlap', 'after'],
                     help='gradient exchange: ONE all-reduce of the flat bucket after backward (default; measured faster: NCCL CTAs '
                          'otherwise take SMs from the 1-CTA/SM backward kernels), or chunked all-reduce overlapped with backward')
@@ -217,7 +220,10 @@ def main():
     bucket = FlatGradBucket(w, overlap=(args.allreduce == 'overlap'))
     bucket.broadcast_parameters(w)
     n_params = sum(p.numel() for p in w.parameters() if p.requires_grad)
-    opt = torch.optim.Adam([p for p in w.parameters() if p.requires_grad], lr=3e-4, betas=(0.9, 0.99), fused=True)
+    if args.optimizer == 'flat':
+        opt = vbx.FlatAdam(bucket, lr=3e-4, betas=(0.9, 0.99), eps=1e-8, max_grad_norm=0.5)
+    else:
+        opt = torch.optim.Adam([p for p in w.parameters() if p.requires_grad], lr=3e-4, betas=(0.9, 0.99), fused=True)
     torch.manual_seed(2 + rank)
     x_host = torch.randn(B, N, D).pin_memory()
     x_dev = x_host.to(dev)
@@ -229,6 +235,9 @@ def main():
         loss = w(x)                                   # ConditionalFlowMatcherWrapper.forward (public API)
         loss.backward()                               # chunked all-reduce overlaps with this (N>1)
         bucket.finish()
+        if args.optimizer == 'flat':                  # clip coefficient + Adam in ONE launch over the flat buffers
+            opt.step()
+            return loss
         gnorm = bucket.flat.norm()                    # clip_grad_norm_(0.5), trainer.py:274-275, on the flat bucket:
         # the clip coefficient c = min(1, 0.5/(norm+1e-6)) is applied INSIDE the fused Adam kernel (its grad_scale input
         # divides every gradient by 1/c) instead of a separate 2 x 2.85 GB scaling pass
@@ -353,7 +362,7 @@ def main():
                     data='synthetic',
                     config=dict(workload=f'VoiceBox dim{D} depth{args.depth} heads{HEADS} seq{N} (+{REG} register tokens) '
                                          f'batch {B}/GPU, CFM loss fwd+bwd+allreduce+clip+Adam', global_batch=B * world,
-                                seq_len=N, parallelism=f'dp{world}', allreduce=args.allreduce, params=n_params, l2='inputs (268 MB/step) exceed the 126 MB L2',
+                                seq_len=N, parallelism=f'dp{world}', allreduce=args.allreduce, optimizer=args.optimizer, params=n_params, l2='inputs (268 MB/step) exceed the 126 MB L2',
                                 peak_mem_gib=round(peak_mem, 1)),
                     e2e=dict(value=e2e_value, unit='frames/s', ms_per_step=ms_e2e / args.steps,
                              h2d_bytes_per_step=x_host.numel() * 4, d2h_bytes_per_step=4),

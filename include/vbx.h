@@ -121,6 +121,23 @@ int vbx_ode_axpy(const float* y, const uint16_t* f, const float* t, int64_t i0, 
                  uint16_t* emb, float* t_out, int64_t B, int64_t N, int64_t D, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Fused gradient clip + Adam step over FLAT buffers              replaces accelerator.clip_grad_norm_ + optim.step()
+ *                                                                 (trainer.py:274-278; optimizer.py:32-35: torch Adam,
+ *                                                                 betas (0.9, 0.99), eps 1e-8; AdamW when wd > 0)
+ * p, g, m, v: f32 [n], 16-byte aligned: every parameter / gradient / first / second moment of the model, each laid out
+ * contiguously in the same order (voicebox-pytorch_b200/dist.py keeps the gradients that way; optim.py the rest).
+ *   g' = g / grad_scale[0]         grad_scale: DEVICE scalar or NULL -- the clip: max(1, (||g||+1e-6)/max_norm)
+ *   g' += weight_decay * p         (decoupled == 0, torch.optim.Adam)    |   p *= 1 - lr*weight_decay  (decoupled != 0, AdamW)
+ *   m = m + (1-beta1)(g' - m);  v = beta2 v + (1-beta2) g'^2
+ *   p -= lr/(1-beta1^step) * m / (sqrt(v)/sqrt(1-beta2^step) + eps)        step is 1-based
+ * found_inf: DEVICE scalar or NULL; when non-zero the launch changes nothing (same contract as torch's fused optimizers).
+ * p_bf16 (bf16 [n], 8-byte aligned, may be NULL) receives the updated parameters rounded to bf16: the tensor-core operand
+ * copies of the next forward, for free.  One pass: 28 B per element (+2). */
+int vbx_adam_step(float* p, const float* g, float* m, float* v, uint16_t* p_bf16, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int decoupled, int64_t step, const float* grad_scale, const float* found_inf,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * qk-RMSNorm + rotary + head split (attention prologue)          replaces vp.py:323-328 (rearrange, q_norm/k_norm,
  *                                                                 apply_rotary_pos_emb) incl. vp.py:193-199, 280-287
  * qkv bf16 [B, N, 3*H*64] (q | k | v blocks, each h-major d-minor, vp.py:320-321);

@@ -333,3 +333,43 @@ def test_argument_errors_are_reported_not_launched(vbx):
         vbx.ops.resid_norm(x, None, torch.ones(12, device='cuda'))
     with pytest.raises(RuntimeError, match='not supported'):
         vbx.ops.resid_norm(torch.randn(1, 2, 4096, device='cuda'), None, torch.ones(4096, device='cuda'))
+
+
+@pytest.mark.skipif(not os.environ.get('VBX_EXPERIMENTAL_TESTS'),
+                    reason='vbx_adam_step has not been seen green on a B200 yet: run with VBX_EXPERIMENTAL_TESTS=1')
+@pytest.mark.parametrize('clip', [None, 0.5])
+def test_flat_adam_matches_torch_adam(vbx, clip):
+    """vbx_adam_step (fused clip + Adam over the flat buffers, trainer.py:274-278) against clip_grad_norm_ + torch.optim.Adam
+    with the reference's hyper-parameters (optimizer.py:13-14), 4 steps, a bucket whose size is not a multiple of 4.
+    fp32 in / fp32 out: 1e-5 relative (fused multiply-adds and one reciprocal differ from ATen's op sequence)."""
+    from voicebox_pytorch_b200.dist import FlatGradBucket
+
+    def make():
+        torch.manual_seed(1)
+        return torch.nn.Sequential(torch.nn.Linear(37, 30), torch.nn.Linear(30, 3)).cuda()
+
+    a, b = make(), make()
+    ref = torch.optim.Adam(a.parameters(), lr=3e-3, betas=(0.9, 0.99), eps=1e-8)
+    bucket = FlatGradBucket(b)
+    opt = vbx.FlatAdam(bucket, lr=3e-3, betas=(0.9, 0.99), eps=1e-8, max_grad_norm=clip, bf16_shadow=True)
+    assert opt.flat_p.numel() % 4 == 1
+    torch.manual_seed(2)
+    for _ in range(4):
+        x = torch.randn(16, 37, device='cuda')
+        ref.zero_grad()
+        a(x).square().sum().backward()
+        if clip is not None:
+            torch.nn.utils.clip_grad_norm_(a.parameters(), clip)
+        ref.step()
+        opt.zero_grad()
+        b(x).square().sum().backward()
+        bucket.finish()
+        opt.step()
+        for pa, pb in zip(a.parameters(), b.parameters()):
+            assert torch.allclose(pa, pb, rtol=1e-5, atol=1e-7)
+    assert torch.equal(opt.flat_p_bf16, opt.flat_p.to(BF16))            # the bf16 operand copy of the next forward
+    assert all(p._version > 0 for p in b.parameters())                   # raw-pointer update is visible to version checks
+    before = opt.flat_p.clone()
+    opt.found_inf = torch.ones(1, device='cuda')                         # skipped step: nothing may change
+    opt.step()
+    assert torch.equal(opt.flat_p, before)

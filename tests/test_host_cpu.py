@@ -235,3 +235,32 @@ def test_batched_gamma_beta_matches_per_norm_linears():
         gbs = ops.batched_affine(cond.to(torch.bfloat16), [w for n in norms for w in (n.to_gamma.weight, n.to_beta.weight)],
                                  [b for n in norms for b in (n.to_gamma.bias, n.to_beta.bias)])
         assert all(torch.equal(a, b) for a, b in zip(gbs, o2)) and not gbs[0].requires_grad
+
+
+def test_flat_adam_repoints_storage_and_keeps_the_module_contract():
+    """optim.FlatAdam moves every parameter into one flat fp32 buffer (same order as the gradient bucket) without
+    changing parameter objects, values, shapes or state_dict keys; stepping without the CUDA library path must raise (no CPU
+    optimizer fallback)."""
+    import torch
+    import voicebox_pytorch_b200 as vbx
+    from voicebox_pytorch_b200.dist import FlatGradBucket
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3))
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    ids = [id(p) for p in m.parameters()]
+    bucket = FlatGradBucket(m)
+    opt = vbx.FlatAdam(bucket, lr=1e-3, max_grad_norm=0.5)
+    assert [id(p) for p in m.parameters()] == ids
+    assert list(m.state_dict().keys()) == list(before.keys())
+    assert all(torch.equal(v, before[k]) for k, v in m.state_dict().items())
+    off = 0
+    for p in bucket.params:   # parameters and gradients are views at the same offsets of their flat buffers
+        assert p.data_ptr() == opt.flat_p.data_ptr() + 4 * off and p.grad.data_ptr() == bucket.flat.data_ptr() + 4 * off
+        off += p.numel()
+    assert off == opt.flat_p.numel() == 7 * 5 + 5 + 5 * 3 + 3
+    m(torch.randn(4, 7)).sum().backward()   # autograd still accumulates into the bucket views
+    assert bucket.flat.abs().sum() > 0
+    with pytest.raises(RuntimeError):
+        opt.step()                          # CPU tensors: the C ABI refuses, nothing is updated
+    with pytest.raises(NotImplementedError):
+        vbx.FlatAdam(bucket, weight_decay=0.01, decoupled=True)

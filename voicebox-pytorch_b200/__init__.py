@@ -20,6 +20,7 @@ from .modules import (  # noqa: F401
     prob_mask_like,
 )
 from .patch import patch_reference  # noqa: F401
+from .optim import FlatAdam  # noqa: F401
 from . import ops, _lib  # noqa: F401
 
 __all__ = ['Transformer', 'VoiceBox', 'DurationPredictor', 'ConditionalFlowMatcherWrapper', 'AudioEncoderDecoder',
