@@ -28,6 +28,14 @@ constexpr uint32_t kTileBytes = kBN * kDh * 2;  // 16 KB
 #ifndef VBX_EXP_TAIL
 #define VBX_EXP_TAIL 0
 #endif
+// EXPERIMENT (backward), off in libvbx_sm100a.so: VBX_EXP_DSBUF=1 double-buffers dS^T in shared memory (paid for by
+// staging dQ one 32-column half at a time) and releases P^T (TMEM) with its own barrier right after the dV GEMM.  In the
+// shipped kernel the compute warps may only store P^T / dS^T of tile i+1 once ALL of tile i's dV/dK/dQ GEMMs have retired,
+// so per tile the GEMM group (~1900 clk in the trace) and the store phase (~800 clk) run back to back; with the flag the
+// stores of tile i+1 overlap the dK/dQ GEMMs of tile i.
+#ifndef VBX_EXP_DSBUF
+#define VBX_EXP_DSBUF 0
+#endif
 
 // ---- optional pipeline trace (built only with -DVBX_TRACE into lib/libvbx_trace.so; tools/trace_attn.py reads it) ----------
 #ifdef VBX_TRACE
@@ -397,13 +405,20 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const uint16_t* __restr
 }
 namespace bwd {
 constexpr int kStages = 3;  // Q/dO ring: the load of tile i+2 is issued as soon as the GEMMs of tile i-1 retire
+constexpr int kDsBufs = VBX_EXP_DSBUF ? 2 : 1;                   // dS^T tiles in shared memory
+constexpr uint32_t kDqStageBytes = VBX_EXP_DSBUF ? 16384 : 32768;  // dQ staging: one 32-column half, or both
 constexpr uint32_t kOffK = 0, kOffV = 16384, kOffQ = 32768, kOffdO = kOffQ + kStages * 16384,
-                   kOffdST = kOffdO + kStages * 16384, kOffdQ = kOffdST + 32768, kOffBar = kOffdQ + 32768,
+                   kOffdST = kOffdO + kStages * 16384, kOffdQ = kOffdST + kDsBufs * 32768, kOffBar = kOffdQ + kDqStageBytes,
                    kOffStat = kOffBar + 128;  // per compute warp, double buffered: [16 warps][2][32 -lse | 32 delta] f32
 constexpr int kComputeWarps = 16;           // 4 threads per key row: 32 query columns of S^T / dP^T each
 constexpr int kProducerWarp = 16, kMmaWarp = 17, kFlushWarp0 = 18;
 constexpr uint32_t kSmemBytes = kOffStat + kComputeWarps * 2 * 64 * 4;  // 204,928 B: one CTA per SM (TMEM: all 512 columns)
-enum { KV_FULL = 0, QD_FULL = 1, QD_EMPTY = 4, ST_FULL = 7, ST_FREE = 8, DS_FULL = 9, DQ_FULL = 10, DQ_FREE = 11, NUM_BARS = 12 };
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+enum { KV_FULL = 0, QD_FULL = 1, QD_EMPTY = 4, ST_FULL = 7, ST_FREE = 8, DS_FULL = 9, DQ_FULL = 10, DQ_FREE = 11,
+       PT_FREE = 12,   // (VBX_EXP_DSBUF) dV_i has retired: P^T may be overwritten, and so may the dS^T buffer of tile i-1
+       ALL_DONE = 13,  // (VBX_EXP_DSBUF) every GEMM of the CTA has retired
+       NUM_BARS = VBX_EXP_DSBUF ? 14 : 12 };
+static_assert(NUM_BARS * 8 + 4 <= 128, "barrier block");
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColST = 0, kColDPT = 128, kColDV = 256, kColDK = 320, kColDQ = 384, kColPT = 448;  // P^T: bf16 pairs
 constexpr int kThreads = 704;  // warps 0-15 compute, 16 TMA producer, 17 MMA issuer, 18-21 dQ flush
@@ -447,6 +462,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
     mbar_init(&bars[DS_FULL], kComputeWarps * 32);
     mbar_init(&bars[DQ_FULL], 1);
     mbar_init(&bars[DQ_FREE], 128);
+    if (VBX_EXP_DSBUF) {
+      mbar_init(&bars[PT_FREE], 1);
+      mbar_init(&bars[ALL_DONE], 1);
+    }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) {
@@ -516,6 +535,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
       for (int i = 0; i < nq; ++i) {
         const int st = i % kStages;
         const uint64_t so = (uint64_t)st * (kTileBytes >> 4);
+        const uint64_t dso = (uint64_t)(i & (kDsBufs - 1)) * (32768 >> 4);  // which dS^T buffer (VBX_EXP_DSBUF)
         if (i + 1 < nq) issue_s(i + 1);  // runs on the tensor pipe while the compute warps finish tile i
         TRACE(0, i, 4);
         mbar_wait(&bars[DS_FULL], i & 1);
@@ -526,10 +546,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
           for (int k = 0; k < kBM / 16; ++k)  // dV += P^T dO   (TS mode: P^T read from TMEM, only dO from shared memory)
             if (!VBX_EXP_TAIL || i < nq - 1 || k * 16 < n_qt)
               umma_bf16_ts(tmem_base + kColDV, tmem_base + kColPT + k * 8, dOmn0 + so + koff_mn(k), idesc_kmn, (i > 0) || (k > 0));
+          if (VBX_EXP_DSBUF) umma_commit(&bars[PT_FREE]);  // dV_i (and everything before it) retired -> P^T is free
 #pragma unroll
           for (int k = 0; k < kBM / 16; ++k)  // dK += dS^T Q
             if (!VBX_EXP_TAIL || i < nq - 1 || k * 16 < n_qt)
-              umma_bf16(tmem_base + kColDK, dSk + koff_k(k), dQmn0 + so + koff_mn(k), idesc_kmn, (i > 0) || (k > 0));
+              umma_bf16(tmem_base + kColDK, dSk + dso + koff_k(k), dQmn0 + so + koff_mn(k), idesc_kmn, (i > 0) || (k > 0));
         }
         __syncwarp();
         mbar_wait(&bars[DQ_FREE], (i & 1) ^ 1);  // the flush warps have read dQ_{i-1} out of TMEM
@@ -537,9 +558,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         if (leader) {
 #pragma unroll
           for (int k = 0; k < kBN / 16; ++k)  // dQ_i = dS K    (A = dS^T read MN-major)
-            umma_bf16(tmem_base + kColDQ, dSmn + koff_mn(k), dKmn + koff_mn(k), idesc_mnmn, k > 0);
+            umma_bf16(tmem_base + kColDQ, dSmn + dso + koff_mn(k), dKmn + koff_mn(k), idesc_mnmn, k > 0);
           umma_commit(&bars[DQ_FULL]);
           umma_commit(&bars[QD_EMPTY + st]);
+          if (VBX_EXP_DSBUF && i == nq - 1) umma_commit(&bars[ALL_DONE]);
         }
         __syncwarp();
         TRACE(0, i, 6);
@@ -552,6 +574,35 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
     // ops (bulk groups are per thread: lane 0 waits for its previous group before the slice is overwritten).
     const int r = (warp & 3) * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+#if VBX_EXP_DSBUF
+    // one 16 KB staging block: the two 32-column halves of dQ_i go through this warp's 4 KB slice one after the other
+    for (int i = 0; i < nq; ++i) {
+      mbar_wait(&bars[DQ_FULL], i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (lane == 0) tma_wait_group_read0();  // the previous reduce-add has read this slice
+        __syncwarp();
+        float v[32];
+        tmem_ld32(t_lane + kColDQ + c * 32, v);
+        if (c == 1) {
+          tc_fence_before();
+          mbar_arrive(&bars[DQ_FREE]);
+        }
+#pragma unroll
+        for (int qd = 0; qd < 8; ++qd) {
+          float4 o4 = make_float4(v[qd * 4] * scale, v[qd * 4 + 1] * scale, v[qd * 4 + 2] * scale, v[qd * 4 + 3] * scale);
+          *reinterpret_cast<float4*>(smem + kOffdQ + r * 128 + ((qd ^ (r & 7)) << 4)) = o4;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_4d(&mdq, smem + kOffdQ + (warp & 3) * 4096, c * 32, i * kBM + (warp & 3) * 32, h, b);
+          tma_commit_group();
+        }
+      }
+    }
+#else
     for (int i = 0; i < nq; ++i) {
       mbar_wait(&bars[DQ_FULL], i & 1);
       tc_fence_after();
@@ -579,6 +630,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         tma_commit_group();
       }
     }
+#endif
     if (lane == 0) tma_wait_group0();
   } else {
     // ------------------------------------------------ compute warps ------------------------------------------------
@@ -652,8 +704,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         for (int x = 0; x < 16; ++x) pk[x] = dsk[x] = 0u;
       }
       if (threadIdx.x == 0) TRACE(1, i, 3);
-      if (i > 0) {  // tile i-1's GEMMs have retired: P^T (TMEM) and dS^T (shared) may be overwritten
-        mbar_wait(&bars[DQ_FULL], (i - 1) & 1);
+      if (i > 0) {
+        // shipped: ALL of tile i-1's GEMMs have retired: P^T (TMEM) and the single dS^T tile (shared) may be overwritten.
+        // VBX_EXP_DSBUF: dV_{i-1} has retired (so has every GEMM of tile i-2): P^T and dS^T buffer i%2 may be overwritten.
+        mbar_wait(&bars[VBX_EXP_DSBUF ? PT_FREE : DQ_FULL], (i - 1) & 1);
         tc_fence_after();
       }
       if (threadIdx.x == 0) TRACE(1, i, 4);
@@ -663,7 +717,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
 #pragma unroll
       for (int qd = 0; qd < 4; ++qd) {
         const int cc = (qr & 1) * 4 + qd;
-        const uint32_t off = (qr >> 1) * kSubTileBytes + r * 128 + ((cc ^ (r & 7)) << 4);
+        const uint32_t off = (i & (kDsBufs - 1)) * 32768 + (qr >> 1) * kSubTileBytes + r * 128 + ((cc ^ (r & 7)) << 4);
         *reinterpret_cast<uint4*>(smem + kOffdST + off) = make_uint4(dsk[qd * 4], dsk[qd * 4 + 1], dsk[qd * 4 + 2], dsk[qd * 4 + 3]);
       }
       tmem_st_wait();
@@ -673,7 +727,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
       mbar_arrive(&bars[DS_FULL]);
       if (threadIdx.x == 0) TRACE(1, i, 6);
     }
-    mbar_wait(&bars[DQ_FULL], (nq - 1) & 1);
+    if (VBX_EXP_DSBUF) mbar_wait(&bars[ALL_DONE], 0);  // these warps did not follow DQ_FULL phase by phase
+    else mbar_wait(&bars[DQ_FULL], (nq - 1) & 1);
     tc_fence_after();
     // all GEMMs have retired: write this thread's 16 columns of dV and dK for its key row.  The TMEM loads are
     // .sync.aligned (whole warp, converged); only the global stores are predicated on the key being real.
