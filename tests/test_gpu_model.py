@@ -220,3 +220,86 @@ def test_full_size_properties_cfg3_one_layer_pair(vbx):
         one = vb(x1[1:], times=t[1:], cond=x1[1:], cond_token_ids=None, cond_drop_prob=0.)
     # different GEMM M may pick a different cuBLAS kernel: equality up to bf16 rounding of the output
     assert maxerr(both[1:], one) <= 2e-2 * float(one.abs().max())
+
+
+# ---- regression tests for the round-1 advisor findings ----------------------------------------------------------------
+class _ToyCodec(torch.nn.Module):
+    """AudioEncoderDecoder duck interface (vp.py:483-592) with latent_dim != dim, so VoiceBox owns a trainable proj_in."""
+    latent_dim, sampling_rate, downsample_factor = 32, 16000, 320
+
+    def encode(self, audio):
+        raise RuntimeError('not used: latents are passed directly')
+
+    def decode(self, latents):
+        return latents
+
+
+def test_trainable_proj_in_receives_gradients(vbx):
+    """vp.py:911-914, 1000, 1007: with audio_enc_dec.latent_dim != dim the reference trains `proj_in`.  The one-pass
+    embed_concat kernel has no grad_fn, so it must not be taken when x / cond carry a graph."""
+    torch.manual_seed(0)
+    vb = vbx.VoiceBox(dim=128, depth=2, heads=2, time_hidden_dim=128, audio_enc_dec=_ToyCodec(), condition_on_text=False)
+    w = vbx.ConditionalFlowMatcherWrapper(voicebox=vb).cuda()
+    assert isinstance(vb.proj_in, torch.nn.Linear)
+    x1 = torch.randn(2, 96, 32, device='cuda')
+    torch.manual_seed(1)
+    loss = w(x1)
+    loss.backward()
+    for n in ('proj_in.weight', 'proj_in.bias', 'to_pred.weight', 'to_embed.weight'):
+        g = dict(vb.named_parameters())[n].grad
+        assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0, n
+    # directional derivative of the loss along d(proj_in.weight): the analytic gradient predicts the finite difference
+    pw = vb.proj_in.weight
+    d = pw.grad / pw.grad.norm()           # steepest direction: the largest signal against the bf16 noise of the loss
+    eps = 5e-2
+    vals = []
+    with torch.no_grad():
+        for sgn in (+1, -1):
+            pw.add_(sgn * eps * d)
+            torch.manual_seed(1)
+            vals.append(float(w(x1)))
+            pw.sub_(sgn * eps * d)
+    fd = (vals[0] - vals[1]) / (2 * eps)
+    an = float((pw.grad * d).sum())
+    assert abs(fd - an) <= 0.25 * max(abs(fd), abs(an)) + 2e-3, (fd, an)
+
+
+def test_sample_then_train_same_length_does_not_cache_inference_tensors(vbx):
+    """sample() runs under inference_mode; rotary tables / bf16 weight copies first seen there used to be cached as
+    inference tensors and a later training step at the same length died in save_for_backward."""
+    torch.manual_seed(0)
+    vb = vbx.VoiceBox(dim=128, depth=2, heads=2, time_hidden_dim=128, condition_on_text=False)
+    for p in vb.to_pred.parameters():
+        p.requires_grad_(False)            # a frozen weight goes through the no-grad bf16 cache in both modes
+    w = vbx.ConditionalFlowMatcherWrapper(voicebox=vb).cuda()
+    cond = torch.randn(2, 77, 128, device='cuda')
+    w.sample(cond=cond, steps=2)
+    loss = w(torch.randn(2, 77, 128, device='cuda'))
+    loss.backward()
+    assert torch.isfinite(loss)
+    w.sample(cond=cond, steps=2)
+
+
+def test_flat_buffers_stay_16_byte_aligned_with_a_one_element_parameter(vbx):
+    """DurationPredictor.to_pred[0].bias has ONE element and comes first in the reversed registration order once the wrapper
+    holds a duration_predictor: every later parameter / gradient view must still start on a 16-byte boundary, or the kernels'
+    float4 accesses fail with VBX_E_ALIGN."""
+    from voicebox_pytorch_b200.dist import FlatGradBucket
+    torch.manual_seed(0)
+    vb = vbx.VoiceBox(dim=128, depth=2, heads=2, time_hidden_dim=128, condition_on_text=False)
+    dp = vbx.DurationPredictor(num_phoneme_tokens=11, dim_phoneme_emb=32, dim=64, depth=2, heads=2)
+    w = vbx.ConditionalFlowMatcherWrapper(voicebox=vb, duration_predictor=dp).cuda()
+    bucket = FlatGradBucket(w)
+    assert bucket.params[0].numel() == 1
+    opt = vbx.FlatAdam(bucket, lr=1e-3, max_grad_norm=0.5)
+    for p in bucket.params:
+        assert p.data_ptr() % 16 == 0 and p.grad.data_ptr() % 16 == 0
+    x1 = torch.randn(2, 64, 128, device='cuda')
+    for _ in range(2):
+        opt.zero_grad()
+        loss = w(x1)
+        loss.backward()
+        bucket.finish()
+        opt.step()
+    assert torch.isfinite(loss)
+    assert float(dp.to_pred[0].bias.grad.abs().max()) == 0   # unused by the CFM loss: stays zero, no unused-parameter pass

@@ -116,7 +116,13 @@ def _worker(rank, world, port, out, overlap=True):
         model[3](model[2](model[1](model[0](xs[0])))).pow(2).mean().backward()
     model[3](model[2](model[1](model[0](xs[1])))).pow(2).mean().backward()
     bucket.finish()
-    out[rank] = bucket.flat.clone()
+    # strip the 16-byte alignment padding between parameters: compare the tightly packed gradients
+    out[rank] = torch.cat([bucket.flat[o:o + p.numel()] for p, o in zip(bucket.params, bucket.offsets)])
+    assert all(o % 4 == 0 for o in bucket.offsets) and bucket.flat.numel() % 4 == 0
+    pad = torch.ones(bucket.flat.numel(), dtype=torch.bool)
+    for p, o in zip(bucket.params, bucket.offsets):
+        pad[o:o + p.numel()] = False
+    assert float(bucket.flat[pad].abs().sum()) == 0          # padding stays zero through accumulation and all-reduce
     # local (un-reduced) reference
     ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 4), torch.nn.Linear(4, 4))
     ref.load_state_dict({k: v for k, v in model.state_dict().items() if not k.startswith('unused')})
@@ -253,11 +259,10 @@ def test_flat_adam_repoints_storage_and_keeps_the_module_contract():
     assert [id(p) for p in m.parameters()] == ids
     assert list(m.state_dict().keys()) == list(before.keys())
     assert all(torch.equal(v, before[k]) for k, v in m.state_dict().items())
-    off = 0
-    for p in bucket.params:   # parameters and gradients are views at the same offsets of their flat buffers
+    for p, off in zip(bucket.params, bucket.offsets):   # parameters and gradients: views at the same, 16-byte aligned offsets
+        assert off % 4 == 0
         assert p.data_ptr() == opt.flat_p.data_ptr() + 4 * off and p.grad.data_ptr() == bucket.flat.data_ptr() + 4 * off
-        off += p.numel()
-    assert off == opt.flat_p.numel() == 7 * 5 + 5 + 5 * 3 + 3
+    assert bucket.offsets == [0, 4, 20, 28] and opt.flat_p.numel() == bucket.flat.numel() == 28 + 36   # sizes 3, 15, 5, 35
     m(torch.randn(4, 7)).sum().backward()   # autograd still accumulates into the bucket views
     assert bucket.flat.abs().sum() > 0
     with pytest.raises(RuntimeError):

@@ -68,6 +68,10 @@ def ptr(t):
         raise RuntimeError('voicebox_pytorch_b200 kernels run on CUDA tensors only (no CPU fallback)')
     if not t.is_contiguous():
         raise RuntimeError('non-contiguous tensor passed to the vbx C ABI')
+    if t.device.index != torch.cuda.current_device():
+        # launches go to torch's current stream of the CURRENT device: a foreign pointer there is an illegal address at best
+        raise RuntimeError(f'tensor on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()}: '
+                           f'wrap the call in torch.cuda.device(...) (one process per GPU is the supported layout)')
     return t.data_ptr()
 
 

@@ -25,18 +25,26 @@ class FlatGradBucket:
         self.params = [p for p in reversed(list(module.parameters())) if p.requires_grad]
         assert self.params, 'no trainable parameters'
         dev = self.params[0].device
-        total = sum(p.numel() for p in self.params)
+        # every parameter starts on a 16-byte boundary (4 floats): the kernels take raw fp32 pointers into this buffer (and into
+        # FlatAdam's parameter buffer, same layout) and use float4 accesses; a 1-element bias must not shift everything after it.
+        # The padding stays zero: it adds nothing to the gradient norm and Adam leaves (p = 0, g = 0) at 0.
+        self.offsets = []
+        off = 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        total = off
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.chunks = []        # (start, end) element offsets
         self._chunk_of = {}     # id(param) -> chunk index
         self._need = []         # parameters per chunk
-        off = start = 0
+        start = 0
         count = 0
-        for p in self.params:
+        for p, o in zip(self.params, self.offsets):
             n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
+            p.grad = self.flat[o:o + n].view_as(p)
             self._chunk_of[id(p)] = len(self.chunks)
-            off += n
+            off = o + (n + 3) // 4 * 4
             count += 1
             if (off - start) * 4 >= chunk_bytes:
                 self.chunks.append((start, off))
@@ -101,15 +109,22 @@ class FlatGradBucket:
     def zero_grad(self):
         """Use instead of optimizer.zero_grad(set_to_none=True), which would detach the .grad views."""
         self.flat.zero_()
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + off * 4:
-                p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+        base = self.flat.data_ptr()
+        for p, off in zip(self.params, self.offsets):
+            if p.grad is None or p.grad.data_ptr() != base + off * 4:
+                p.grad = self.flat[off:off + p.numel()].view_as(p)
 
     def broadcast_parameters(self, module, src=0):
         """Initial replica sync (DDP does this at construction)."""
         if self.world > 1:
+            # one collective per dtype instead of one per tensor (~400 at depth 24)
+            by_dtype = {}
             for t in list(module.parameters()) + list(module.buffers()):
-                dist.broadcast(t.data, src=src, group=self.group)
+                by_dtype.setdefault(t.dtype, []).append(t.data)
+            for dtype, ts in by_dtype.items():
+                flat = torch.cat([t.reshape(-1) for t in ts])
+                dist.broadcast(flat, src=src, group=self.group)
+                off = 0
+                for t in ts:
+                    t.copy_(flat[off:off + t.numel()].view_as(t))
+                    off += t.numel()

@@ -318,7 +318,9 @@ def _rotary_tables(self, n, device):
     key = (n, r, str(device))
     hit = cache.get(key)
     if hit is None:
-        with torch.no_grad():
+        # sample() runs under inference_mode: tensors created there cannot be saved for a later backward, so the table is
+        # always built as a normal (non-inference) tensor
+        with torch.inference_mode(False), torch.no_grad():
             pos = torch.arange(n, device=device, dtype=torch.long)
             if r:
                 pos = torch.cat((torch.full((r,), -10000, device=device, dtype=torch.long), pos))
@@ -506,7 +508,10 @@ def voicebox_forward(self, x, *, times, cond_token_ids, self_attn_mask=None, con
         else:
             cond_mask = torch.ones((batch, seq_len), device=cond.device, dtype=torch.bool)
 
-    if not self.condition_on_text and not cond_drop_prob > 0.:
+    # The one-pass kernel writes through raw pointers (no grad_fn): only when nothing upstream can need a gradient.  With a
+    # trainable proj_in (audio_enc_dec.latent_dim != dim, vp.py:911-914) x / cond carry a graph and take the torch route below.
+    upstream_grad = torch.is_grad_enabled() and (x.requires_grad or cond.requires_grad)
+    if not self.condition_on_text and not cond_drop_prob > 0. and not upstream_grad:
         emb = ops.embed_concat(x, cond, cond_mask)            # cond * ~mask, cat, bf16 cast: one pass
     else:
         cond = cond * ~cond_mask[..., None]
@@ -689,7 +694,11 @@ class ConditionalFlowMatcherWrapper(nn.Module):
         path = Path(path)
         assert path.exists()
         pkg = torch.load(str(path), map_location='cpu')
-        self.load_state_dict(pkg['model'], strict=strict)
+        # the reference DurationPredictor owns a third-party `aligner` (vp.py:682-683) that this mirror does not build: its
+        # keys are the one documented exception to the state_dict contract and are skipped, not failed on
+        own = set(self.state_dict().keys())
+        model = {k: v for k, v in pkg['model'].items() if k in own or '.aligner.' not in '.' + k}
+        self.load_state_dict(model, strict=strict)
         return pkg
 
     forward = None

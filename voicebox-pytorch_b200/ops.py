@@ -18,6 +18,16 @@ def _c(t):
     return t if t is None or t.is_contiguous() else t.contiguous()
 
 
+def _m(mask):
+    """Masks cross the C ABI as one byte per element (0 / 1): anything that is not torch.bool is converted first (a float or
+    long mask read as bytes would be silently wrong)."""
+    if mask is None:
+        return None
+    if mask.dtype != torch.bool:
+        mask = mask.to(torch.bool)
+    return _c(mask)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # bf16 operand cache: fp32 master parameters are cast to bf16 at use (what autocast does every forward, trainer.py:267);
 # under no_grad (sampling: 2 evaluations per solver step with constant weights) the cast is cached per parameter version.
@@ -39,7 +49,7 @@ def cast_bf16(p, tag='', transform=None):
     # addresses and version counters) are reused once a model is freed and another one is built
     if hit is not None and hit[0]() is p and hit[1] == p._version and hit[2] == p.data_ptr():
         return hit[3]
-    with torch.no_grad():
+    with torch.inference_mode(False), torch.no_grad():  # never cache an inference tensor (sample-then-train)
         q = p.detach().to(BF16)
         q = transform(q) if transform is not None else q
     if len(_cast_cache) > 4096:  # entries of freed models are only dropped here
@@ -83,7 +93,7 @@ def stack_cast_bf16(ps, tag=''):
     hit = _stack_cache.get(key)
     if hit is not None and hit[0]() is ps[0] and hit[1] == sig:
         return hit[2]
-    with torch.no_grad():
+    with torch.inference_mode(False), torch.no_grad():
         q = _StackCastBf16.forward(None, *ps)
     _stack_cache[key] = (weakref.ref(ps[0]), sig, q)
     return q
@@ -253,7 +263,7 @@ def linear_geglu(x, w_bf16, b_bf16):
 class _ConvPos(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, mask, reg):
-        x, mask = _c(x), _c(mask)
+        x, mask = _c(x), _m(mask)
         B, N, C = x.shape
         K = weight.shape[-1]
         w2 = _c(weight.reshape(C, K).float())
@@ -295,7 +305,7 @@ def convpos_residual_pack(x, weight, bias, mask=None, register_tokens=None):
 class _Attention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, cosv, sinv, gq, gk, key_mask, scale, heads):
-        qkv, key_mask = _c(qkv), _c(key_mask)
+        qkv, key_mask = _c(qkv), _m(key_mask)
         B, N, three_hd = qkv.shape
         H = heads
         hd = three_hd // 3
@@ -353,7 +363,7 @@ def attention(qkv, cosv, sinv, q_gamma, k_gamma, key_mask, scale, heads):
 def cfm_embed(x0, x1, times, cond_mask, sigma):
     """-> bf16 [B,N,2D] = [ w | flow * ~cond_mask ]   (vp.py:1408-1410, 1003, 1035, 1075-1076).  Not differentiable
     (the data does not require grad)."""
-    x0, x1, cond_mask = _c(x0.float()), _c(x1.float()), _c(cond_mask)
+    x0, x1, cond_mask = _c(x0.float()), _c(x1.float()), _m(cond_mask)
     B, N, D = x1.shape
     emb = torch.empty((B, N, 2 * D), device=x1.device, dtype=BF16)
     call('vbx_cfm_embed', ptr(x0), ptr(x1), ptr(_c(times.float())), ptr(cond_mask), float(sigma), ptr(emb), B, N, D, stream())
@@ -368,14 +378,14 @@ def embed_concat(x, cond, cond_mask, out=None):
         out = torch.empty((B, N, 2 * D), device=ref.device, dtype=BF16)
     x = None if x is None else _c(x.float())
     cond = None if cond is None else _c(cond.float())
-    call('vbx_embed_concat', ptr(x), ptr(cond), ptr(_c(cond_mask)), ptr(out), B, N, D, stream())
+    call('vbx_embed_concat', ptr(x), ptr(cond), ptr(_m(cond_mask)), ptr(out), B, N, D, stream())
     return out
 
 
 class _MaskedMse(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, tgt, x0, x1, sigma, loss_mask):
-        pred, loss_mask = _c(pred), _c(loss_mask)
+        pred, loss_mask = _c(pred), _m(loss_mask)
         B, N, D = pred.shape
         num = torch.zeros((B,), device=pred.device, dtype=torch.float32)
         call('vbx_masked_mse_fwd', ptr(pred), ptr(tgt), ptr(x0), ptr(x1), float(sigma), ptr(loss_mask), ptr(num), B, N, D, stream())

@@ -28,14 +28,12 @@ class FlatAdam:
         total = bucket.flat.numel()
         dev = bucket.flat.device
         self.flat_p = torch.empty(total, dtype=torch.float32, device=dev)
-        off = 0
+        self.flat_p.zero_()             # alignment padding between parameters (bucket.offsets) stays zero forever
         with torch.no_grad():
-            for p in params:
-                n = p.numel()
-                view = self.flat_p[off:off + n].view_as(p)
+            for p, off in zip(params, bucket.offsets):
+                view = self.flat_p[off:off + p.numel()].view_as(p)
                 view.copy_(p)
                 p.data = view           # same nn.Parameter object (module attributes, optimizer-free), new storage
-                off += n
         self.exp_avg = torch.zeros_like(self.flat_p)
         self.exp_avg_sq = torch.zeros_like(self.flat_p)
         self.flat_p_bf16 = torch.empty(total, dtype=torch.bfloat16, device=dev) if bf16_shadow else None
