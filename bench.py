@@ -66,60 +66,236 @@ def oracle_state(depth=DEPTH, seed=0):
     return {k: v.detach() for k, v in w.state_dict().items()}
 
 
-CPU_SAMPLE_DEPTH = 2   # layers timed on the CPU; the full model has DEPTH of them
+CPU_DEPTHS = (2, 6)    # layer counts timed on the CPU; the full model (DEPTH layers) is the two-point linear extrapolation
+CPU_BATCH = 2          # cfg3 at reduced batch B=2, per-sample cost scaled linearly
 
 
-def cpu_reference_frames_per_sec(batch=1, steps=1, warmup=1):
-    """fp32 forward+backward of the CFM loss through oracle/voicebox_oracle.py on all host threads, on a BOUNDED sample of the
-    workload: same width / heads / sequence, batch 1, CPU_SAMPLE_DEPTH of the DEPTH transformer layers.  The per-layer cost
-    dominates (embedding, conv and loss are < 3 % of a layer pair), CPU time is linear in depth and batch at these sizes, so
-    frames/s of the full model = batch*SEQ / (t_sample * DEPTH / CPU_SAMPLE_DEPTH); the fixed parts are over-counted by that
-    scaling, i.e. the CPU figure is slightly pessimistic.  (A full-depth step takes minutes on a 128-thread host.)"""
-    from oracle import voicebox_oracle as O
+def _host_cores():
     try:
-        cores = len(os.sched_getaffinity(0))
+        return len(os.sched_getaffinity(0))
     except Exception:
-        cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    sd = oracle_state(depth=CPU_SAMPLE_DEPTH)
-    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'null_cond' not in k and 'inv_freq' not in k else v)
-           for k, v in sd.items()}
-    cfg = dict(depth=CPU_SAMPLE_DEPTH, heads=HEADS, num_register_tokens=REG, qk_norm=True, condition_on_text=False)
+        return os.cpu_count() or 1
+
+
+def _cpu_step_fn(depth, flash, batch):
+    """-> (callable running ONE fp32 forward+backward of the CFM loss on the CPU, kind).  kind 'reference': the UNMODIFIED
+    reference package (baseline/_ref or /root/reference, stub-imported by oracle/ref_import.py) through its own public API
+    `ConditionalFlowMatcherWrapper(x)`; kind 'port': oracle/voicebox_oracle.py (math-path attention only) when no copy of the
+    reference is on the box."""
     x1 = torch.randn(batch, SEQ, DIM)
-    times = []
-    for i in range(warmup + steps):
+    try:
+        from oracle import ref_import
+        if ref_import.reference_root() is None:
+            raise ImportError('no reference copy')
+        vp = ref_import.import_reference()
+        torch.manual_seed(0)
+        vb = vp.VoiceBox(dim=DIM, depth=depth, heads=HEADS, dim_head=64, attn_flash=flash, condition_on_text=False, num_cond_tokens=None)
+        g = torch.Generator().manual_seed(1)
+        with torch.no_grad():
+            for n, p in vb.named_parameters():
+                if 'to_gamma.weight' in n or 'to_beta.weight' in n:
+                    p.normal_(0, 0.02, generator=g)
+        w = vp.ConditionalFlowMatcherWrapper(voicebox=vb)
+
+        def step():
+            w.zero_grad(set_to_none=True)
+            w(x1).backward()
+        return step, 'reference'
+    except Exception as ex:
+        if flash:
+            raise RuntimeError(f'attn_flash=True needs the reference package on the box ({ex!r})')
+        from oracle import voicebox_oracle as O
+        sd = oracle_state(depth=depth)
+        sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'null_cond' not in k and 'inv_freq' not in k else v)
+               for k, v in sd.items()}
+        cfg = dict(depth=depth, heads=HEADS, num_register_tokens=REG, qk_norm=True, condition_on_text=False)
+
+        def step():
+            for v in sdg.values():
+                if v.grad is not None:
+                    v.grad = None
+            O.cfm_loss(sdg, cfg, x1).backward()
+        return step, 'port'
+
+
+def _median_step_seconds(step, warmup, steps):
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
         t0 = time.perf_counter()
-        loss = O.cfm_loss(sdg, cfg, x1)
-        loss.backward()
-        dt = time.perf_counter() - t0
-        for v in sdg.values():
-            if v.grad is not None:
-                v.grad = None
-        if i >= warmup:
-            times.append(dt)
-        elif dt > 15.0:      # slow host: keep the sample bounded, count the (cold) first step instead of repeating it
-            times.append(dt)
-            warmup, steps = 0, 1
-            break
-    sec = statistics.median(times) * DEPTH / CPU_SAMPLE_DEPTH
-    return dict(value=batch * SEQ / sec, unit='frames/s', cores=cores, kind='port',
-                sample=f'oracle fp32 fwd+bwd, dim{DIM} seq{SEQ} batch {batch}, {CPU_SAMPLE_DEPTH} of {DEPTH} layers timed '
-                       f'({statistics.median(times):.2f} s, {steps} step(s) after {warmup} warm-up) and scaled x{DEPTH // CPU_SAMPLE_DEPTH} '
-                       f'in depth -> {sec:.1f} s per full step, threads={torch.get_num_threads()}'), sec
+        step()
+        ts.append(time.perf_counter() - t0)
+    return statistics.median(ts), ts
+
+
+def cpu_reference_frames_per_sec(flash=False, steps=3, warmup=2):
+    """The reference's CPU path on all host threads, fp32, on a BOUNDED sample of the cfg3 workload: full width / heads /
+    sequence at batch CPU_BATCH, with CPU_DEPTHS = (2, 6) of the 24 identical layers timed (always `warmup` >= 2 untimed steps,
+    median of `steps` >= 3).  The per-layer cost is (t6 - t2) / 4 and the depth-independent part (embedding, conv, time MLP,
+    to_pred, loss) is t2 - 2 * per_layer, so the full model is fixed + 24 * per_layer -- no cold iteration is ever counted.
+    frames/s = CPU_BATCH * SEQ / full_step_seconds."""
+    cores = _host_cores()
+    torch.set_num_threads(cores)
+    warmup, steps = max(2, warmup), max(3, steps)
+    med, raw, kind = {}, {}, None
+    for d in CPU_DEPTHS:
+        fn, kind = _cpu_step_fn(d, flash, CPU_BATCH)
+        med[d], raw[d] = _median_step_seconds(fn, warmup, steps)
+        del fn
+    d0, d1 = CPU_DEPTHS
+    per_layer = max((med[d1] - med[d0]) / (d1 - d0), 1e-9)
+    fixed = max(med[d0] - d0 * per_layer, 0.0)
+    full = fixed + DEPTH * per_layer
+    sampled = sum(sum(v) for v in raw.values())
+    return dict(value=CPU_BATCH * SEQ / full, unit='frames/s', cores=cores, kind=kind, attn_flash=bool(flash),
+                est_full_step_s=full, per_layer_s=per_layer, fixed_s=fixed, timed_s={str(k): v for k, v in med.items()},
+                sample=f'{"reference package" if kind == "reference" else "oracle port"} fp32 fwd+bwd of the CFM loss, dim{DIM} seq{SEQ} heads{HEADS} '
+                       f'batch {CPU_BATCH}, attn_flash={bool(flash)}: depth {d0} -> {med[d0]:.2f} s, depth {d1} -> {med[d1]:.2f} s (median of {steps} '
+                       f'after {warmup} warm-ups each) => {per_layer:.3f} s/layer + {fixed:.2f} s fixed => {full:.1f} s per full-depth step; '
+                       f'{sampled:.0f} s of timed CPU work, threads={torch.get_num_threads()}'), full
 
 
 def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (rank 0 only).  A 'step' of this
+    arm is one bounded sample (see cpu_reference_frames_per_sec); `steps` / `ms_per_step` describe what actually ran."""
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    base, sec = cpu_reference_frames_per_sec(batch=1, steps=max(1, min(args.steps, 3)), warmup=1)
-    line = dict(metric=METRIC, value=base['value'], unit='frames/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='fp32', data='synthetic',
-                impl='reference',
-                config=dict(workload=f'VoiceBox dim{DIM} depth{DEPTH} heads{HEADS} seq{SEQ} CFM train step; CPU sample: batch 1, '
-                                     f'{CPU_SAMPLE_DEPTH}/{DEPTH} layers timed and scaled (see cpu_baseline.sample)'),
-                cpu_baseline=base, e2e=dict(value=base['value'], unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    steps = max(3, min(args.steps, 3))
+    t_start = time.perf_counter()
+    res = {}
+    for flash in (True, False):
+        try:
+            res[flash], _ = cpu_reference_frames_per_sec(flash=flash, steps=steps, warmup=2)
+        except Exception as ex:
+            res[flash] = dict(value=None, error=repr(ex))
+    best = max((r for r in res.values() if r.get('value')), key=lambda r: r['value'])
+    n_timed = steps * len(CPU_DEPTHS) * sum(1 for r in res.values() if r.get('value'))
+    wall = time.perf_counter() - t_start
+    line = dict(metric=METRIC, value=best['value'], unit='frames/s', n_gpus=args.gpus, steps=n_timed, warmup=2,
+                ms_per_step=wall * 1e3 / max(n_timed, 1), higher_is_better=True, scaling='weak', vs_baseline=None, dtype='fp32',
+                data='synthetic', impl='reference',
+                config=dict(workload=f'VoiceBox dim{DIM} depth{DEPTH} heads{HEADS} seq{SEQ} CFM train step on the host CPU; bounded '
+                                     f'sample: batch {CPU_BATCH}, depths {CPU_DEPTHS} timed, linear in depth (see cpu_baseline.sample); '
+                                     f'steps = timed sample-steps actually run, ms_per_step = wall time of the whole arm / steps',
+                            est_full_step_s=best['est_full_step_s']),
+                cpu_baseline=best, attn_flash_true=res[True], attn_flash_false=res[False],
+                e2e=dict(value=best['value'], unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)
+
+
+def _time_cuda(fn, iters=5, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3   # us
+
+
+def sdpa_baseline(B, H, Np, dev):
+    """torch.nn.functional.scaled_dot_product_attention on THIS GPU at the bench geometry (bf16 q,k,v [B,H,N',64], already
+    normed / rotated, scale 10 as in the trunk): what the reference's `attn_flash=True` path reaches (attend.py:71-98) per
+    backend.  fwd_us = forward alone; bwd_us = (forward+backward) - forward, the number to hold vbx_attn_bwd against."""
+    import torch.nn.functional as F
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+    q, k, v = (torch.randn(B, H, Np, 64, device=dev, dtype=torch.bfloat16, requires_grad=True) for _ in range(3))
+    do = torch.randn(B, H, Np, 64, device=dev, dtype=torch.bfloat16)
+    out = {}
+    for name, be in (('cudnn', SDPBackend.CUDNN_ATTENTION), ('flash', SDPBackend.FLASH_ATTENTION),
+                     ('mem_efficient', SDPBackend.EFFICIENT_ATTENTION)):
+        try:
+            with sdpa_kernel(be):
+                def fwd():
+                    with torch.no_grad():
+                        return F.scaled_dot_product_attention(q, k, v, scale=10.0)
+
+                def fwdbwd():
+                    o = F.scaled_dot_product_attention(q, k, v, scale=10.0)
+                    o.backward(do)
+                    q.grad = k.grad = v.grad = None
+                f_us, fb_us = _time_cuda(fwd), _time_cuda(fwdbwd)
+            fl = 4.0 * B * H * Np * Np * 64
+            out[name] = dict(fwd_us=f_us, bwd_us=fb_us - f_us, fwd_tflops=fl / f_us / 1e6, bwd_tflops=2.5 * fl / (fb_us - f_us) / 1e6)
+        except Exception as ex:
+            out[name] = f'unavailable: {type(ex).__name__}: {str(ex)[:120]}'
+    return out
+
+
+def run_durpred(args):
+    """BASELINE configs[4]: DurationPredictor transformer dim 512, depth 10, heads 8, seq 512, batch 128 per GPU, eval forward
+    (conv positional embedding + plain-RMSNorm trunk with key-padding mask, bf16 residual in the reference).  Replicas only:
+    every rank runs its own batch, no collective on the data path.  value = phoneme positions/s over all ranks."""
+    import torch.distributed as dist
+    import voicebox_pytorch_b200 as vbx
+    rank, local, world = (int(os.environ.get(k, 0)) for k in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE'))
+    world = max(world, 1)
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        dist.init_process_group('nccl', device_id=dev)
+    Bd, Nd, Dd = 128, 512, 512
+    torch.manual_seed(0)
+    dp = vbx.DurationPredictor(num_phoneme_tokens=256, dim_phoneme_emb=512, dim=Dd, depth=10, heads=8).to(dev).eval()
+    torch.manual_seed(3 + rank)
+    ids_host = torch.randint(0, 256, (Bd, Nd))
+    for b in range(Bd):
+        pad = int(torch.randint(0, 128, (1,)))
+        if pad:
+            ids_host[b, Nd - pad:] = -1
+    ids_host = ids_host.pin_memory()
+    cond_host = torch.randn(Bd, Nd, Dd).pin_memory()
+    cmask = torch.zeros(Bd, Nd, dtype=torch.bool, device=dev)
+    ids, cond = ids_host.to(dev), cond_host.to(dev)
+
+    def fwd():
+        with torch.no_grad():
+            return dp(cond=cond, phoneme_ids=ids, cond_mask=cmask)
+
+    def fwd_e2e():
+        with torch.no_grad():
+            return dp(cond=cond_host.to(dev, non_blocking=True), phoneme_ids=ids_host.to(dev, non_blocking=True), cond_mask=cmask).cpu()
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+    for _ in range(max(args.warmup, 3)):
+        fwd()
+    l0 = vbx._lib.launch_count
+    ms = timed(fwd, args.steps)
+    launches = vbx._lib.launch_count - l0
+    fwd_e2e()
+    ms_e2e = timed(fwd_e2e, args.steps)
+    if rank == 0:
+        units = Bd * Nd * world * args.steps
+        line = dict(metric='durpred_eval_positions_per_sec', value=units / (ms / 1e3), unit='positions/s', n_gpus=world, steps=args.steps,
+                    warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype='bf16', data='synthetic', gpu_launches=launches,
+                    tflops=4.881 * world * args.steps / (ms / 1e3) / 1e0,
+                    config=dict(workload=f'DurationPredictor dim{Dd} depth10 heads8 seq{Nd} batch {Bd}/GPU eval forward (BASELINE configs[4]), '
+                                         f'replicas only', parallelism=f'replicas{world}', l2='activations (134 MB per tensor) exceed L2'),
+                    e2e=dict(value=units / (ms_e2e / 1e3), unit='positions/s', h2d_bytes_per_step=cond_host.numel() * 4 + ids_host.numel() * 8,
+                             d2h_bytes_per_step=Bd * Nd * 4))
+        print(json.dumps(line), file=_REAL_STDOUT, flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -176,6 +352,10 @@ def main():
                     help='gradient exchange: ONE all-reduce of the flat bucket after backward (default; measured faster: NCCL CTAs '
                          'otherwise take SMs from the 1-CTA/SM backward kernels), or chunked all-reduce overlapped with backward')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-sdpa', action='store_true')
+    ap.add_argument('--sample-steps', type=int, default=64, help='midpoint solver steps timed in the sampling leg (configs[3]: 64)')
+    ap.add_argument('--workload', default='train', choices=['train', 'durpred'],
+                    help="'durpred': BASELINE configs[4] -- DurationPredictor dim512 depth10 seq512 batch 128/GPU eval forward, replicas")
     ap.add_argument('--profile-only', action='store_true',
                     help='for ncu launch lists only: allows --warmup < 3, skips the e2e / sampling / CPU legs; the printed number is NOT a bench value')
     args = ap.parse_args()
@@ -187,6 +367,8 @@ def main():
     os.dup2(2, 1)
     if args.impl == 'reference':
         return run_reference_arm(args)
+    if args.workload == 'durpred':
+        return run_durpred(args)
     assert args.warmup >= 3 or args.profile_only, 'timing rules: at least 3 warm-up steps'
     if args.profile_only:
         args.no_sample = args.no_cpu_baseline = True
@@ -330,7 +512,20 @@ def main():
                         traffic=traffic, peak_source=peaks['source'] + (' sustained bf16' if k['bound'] == 'tensor' else ' hbm copy'),
                         share_of_step=k['ms_per_step'] / (ms_dev / args.steps))
 
-    # ---- sampling (BASELINE configs[3]) ---------------------------------------------------------------------------------
+    # ---- same-box SDPA baseline for the attention kernels (what the reference's attn_flash=True reaches on this GPU) --------
+    sdpa = None
+    if rank == 0 and not args.profile_only and not args.no_sdpa:
+        try:
+            sdpa = sdpa_baseline(B, HEADS, N + REG, dev)
+            for kname, key in (('vbx_attn_fwd', 'fwd_us'), ('vbx_attn_bwd', 'bwd_us')):
+                if kname in kernels:
+                    best = min((v[key] for v in sdpa.values() if isinstance(v, dict) and v.get(key)), default=None)
+                    kernels[kname]['sdpa_us'] = {b: (v.get(key) if isinstance(v, dict) else v) for b, v in sdpa.items()}
+                    kernels[kname]['speedup_vs_best_sdpa'] = (best / kernels[kname]['avg_us']) if best else None
+        except Exception as ex:
+            sdpa = dict(error=repr(ex))
+
+    # ---- sampling (BASELINE configs[3]): all 64 midpoint steps, CUDA-graph replay of one captured solver step ---------------
     sample = None
     if not args.no_sample:
         del opt
@@ -338,23 +533,35 @@ def main():
         for p in w.parameters():
             p.grad = None
         torch.cuda.empty_cache()
-        SB, SN, solver_steps = 16, 2048, 4
-        cond = torch.randn(SB, SN, D, device=dev)
+        from voicebox_pytorch_b200 import ode as vode
+        SB, SN, solver_steps = 16, 2048, args.sample_steps
+        cond_host = torch.randn(SB, SN, D).pin_memory()
         cmask = torch.zeros(SB, SN, dtype=torch.bool, device=dev)
         cmask[:, int(0.3 * SN):] = True
-        w.sample(cond=cond, cond_mask=cmask, steps=2)            # warm-up: 1 solver step (weights cast + cached)
-        w.sample(cond=cond, cond_mask=cmask, steps=2)
+        cond = cond_host.to(dev)
+        w.sample(cond=cond, cond_mask=cmask, steps=6)            # warm-up: weights cast + cached, one solver step captured
         ms_s = timed(lambda: w.sample(cond=cond, cond_mask=cmask, steps=solver_steps + 1), 1)
+        info = dict(vode.last_run_info)
+
+        def sample_e2e():                                       # public API, host conditioning in, host sample out
+            out = w.sample(cond=cond_host.to(dev, non_blocking=True), cond_mask=cmask, steps=solver_steps + 1)
+            return out.cpu()
+        ms_s_e2e = timed(sample_e2e, 1)
+        nfe_tflop = 26.864 * (args.depth / DEPTH)               # per evaluation at B=16, N=2048
         sample = dict(metric='sample_ode_steps_per_sec', value=world * solver_steps / (ms_s / 1e3), unit='ODE-steps/s',
-                      ms_per_ode_step=ms_s / solver_steps,
+                      ms_per_ode_step=ms_s / solver_steps, solver_steps_timed=solver_steps, cuda_graph=info,
+                      tflops=2 * nfe_tflop * solver_steps / (ms_s / 1e3),
+                      frac_of_sustained_bf16=(2 * nfe_tflop * solver_steps / (ms_s / 1e3)) / peaks['tf_sustained'],
+                      e2e=dict(value=world * solver_steps / (ms_s_e2e / 1e3), unit='ODE-steps/s',
+                               h2d_bytes_per_call=cond_host.numel() * 4, d2h_bytes_per_call=cond_host.numel() * 4),
                       config=dict(workload=f'ConditionalFlowMatcherWrapper.sample dim{D} depth{args.depth} seq{SN} batch {SB}/GPU '
-                                           f'midpoint (2 NFE/step), cond masked 70%, {solver_steps} timed solver steps of the 64'))
+                                           f'midpoint (2 NFE/step), cond masked 70%, all {solver_steps} solver steps timed'))
 
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline and args.depth == DEPTH:
             try:
-                cpu, _ = cpu_reference_frames_per_sec(batch=1, steps=1, warmup=1)
+                cpu, _ = cpu_reference_frames_per_sec(flash=True, steps=3, warmup=2)
             except Exception as ex:  # the baseline must never take the GPU number down with it
                 cpu = dict(value=None, unit='frames/s', cores=os.cpu_count(), kind='port', sample=f'failed: {ex!r}')
         line = dict(metric=METRIC, value=value, unit='frames/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -366,7 +573,8 @@ def main():
                                 peak_mem_gib=round(peak_mem, 1)),
                     e2e=dict(value=e2e_value, unit='frames/s', ms_per_step=ms_e2e / args.steps,
                              h2d_bytes_per_step=x_host.numel() * 4, d2h_bytes_per_step=4),
-                    profile_only=bool(args.profile_only), gpu_launches=launches, roofline=roofline, kernels=kernels, clocks=clocks, sample=sample, cpu_baseline=cpu)
+                    profile_only=bool(args.profile_only), gpu_launches=launches, roofline=roofline, kernels=kernels, sdpa_baseline=sdpa, clocks=clocks,
+                    sample=sample, cpu_baseline=cpu)
         print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -1,8 +1,11 @@
-"""Import the UNMODIFIED reference (lucidrains/voicebox-pytorch) read-only from /root/reference.
+"""Import the UNMODIFIED reference (lucidrains/voicebox-pytorch) read-only: from /root/reference in the build container,
+else from baseline/_ref (the `pip install --no-deps --target baseline/_ref` copy of the task contract: git-ignored, it
+travels to the GPU box with the snapshot).
 
-TEST INFRASTRUCTURE ONLY.  Used in this container to (a) validate oracle/voicebox_oracle.py and
-(b) generate tests/golden/*.npz (tests/golden/make_golden.py).  /root/reference does not exist on the
-GPU box, so nothing under `-m gpu`, smoke() or bench.py imports this module.
+TEST INFRASTRUCTURE ONLY.  Used in the build container to (a) validate oracle/voicebox_oracle.py and (b) generate
+tests/golden/*.npz (tests/golden/make_golden.py); on the GPU box only by tests/test_gpu_patch_reference.py, which
+builds REFERENCE objects and rebinds them with `patch_reference` (skipped, loudly, when no copy is present).
+smoke() and bench.py never import this module.
 
 The reference cannot be imported as shipped: seven third-party packages it imports at module scope are
 absent here.  None of them is on the hot path, so they are replaced by inert
@@ -16,7 +19,21 @@ import warnings
 import torch
 from torch import nn
 
-REFERENCE_ROOT = '/root/reference'
+import os
+
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CANDIDATES = ('/root/reference', os.path.join(_REPO, 'baseline', '_ref'))
+
+
+def reference_root():
+    """First directory that holds the reference package, or None."""
+    for root in _CANDIDATES:
+        if os.path.isfile(os.path.join(root, 'voicebox_pytorch', 'voicebox_pytorch.py')):
+            return root
+    return None
+
+
+REFERENCE_ROOT = reference_root() or '/root/reference'
 
 
 def _mod(name, **attrs):

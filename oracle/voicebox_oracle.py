@@ -297,8 +297,8 @@ def odeint_fixed_grid(fn, y0, t, *, method='midpoint', atol=None, rtol=None, **_
     """Restatement of torchdiffeq.odeint for its fixed-grid 'euler' and 'midpoint' solvers (un-vendored dependency;
     call site vp.py:1295).  The grid is the user's `t`; t0/t1 are 0-dim tensor slices of t; atol/rtol are accepted and
     ignored by fixed-grid solvers; the solution at every grid point is returned stacked (caller takes [-1])."""
-    if method not in ('euler', 'midpoint'):
-        raise NotImplementedError(f'only fixed-grid euler/midpoint are on the hot path, got {method!r}')
+    if method not in ('euler', 'midpoint', 'rk4'):
+        raise NotImplementedError(f'only the fixed-grid solvers euler/midpoint/rk4 are on the hot path, got {method!r}')
     ys = [y0]
     y = y0
     for i in range(t.shape[0] - 1):
@@ -307,6 +307,12 @@ def odeint_fixed_grid(fn, y0, t, *, method='midpoint', atol=None, rtol=None, **_
         f0 = fn(t0, y)
         if method == 'euler':
             dy = dt * f0
+        elif method == 'rk4':
+            # torchdiffeq RK4._step_func -> rk4_alt_step_func: the 3/8 rule ("smaller error with slightly more compute")
+            k2 = fn(t0 + dt / 3, y + dt * f0 / 3)
+            k3 = fn(t0 + dt * 2 / 3, y + dt * (k2 - f0 / 3))
+            k4 = fn(t1, y + dt * (f0 - k2 + k3))
+            dy = dt * (f0 + 3 * (k2 + k3) + k4) / 8
         else:
             half_dt = 0.5 * dt
             dy = dt * fn(t0 + half_dt, y + f0 * half_dt)

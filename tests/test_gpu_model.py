@@ -303,3 +303,39 @@ def test_flat_buffers_stay_16_byte_aligned_with_a_one_element_parameter(vbx):
         opt.step()
     assert torch.isfinite(loss)
     assert float(dp.to_pred[0].bias.grad.abs().max()) == 0   # unused by the CFM loss: stays zero, no unused-parameter pass
+
+
+def test_sampling_rk4_and_graph_replay_vs_oracle(vbx):
+    """(a) fixed-grid rk4 (torchdiffeq's 3/8 rule, SURVEY 8f-4) against the oracle's restatement on the same y0;
+    (b) a 9-point midpoint trajectory runs as CUDA-graph replays of one captured solver step (ode.last_run_info) and equals
+    the eager loop (VBX_ODE_GRAPH=0) to bf16 re-association noise."""
+    import os
+    a, sd, w, cfg = build(vbx, 'voicebox_d128_l2_h4_n200_noqknorm')
+    real = torch.randn_like
+    torch.randn_like = lambda ref, **kw: a['y0'].clone()
+    try:
+        w.odeint_kwargs['method'] = 'rk4'
+        out = w.sample(cond=a['cond'], cond_mask=a['sample_cond_mask'], steps=3)
+        with torch.no_grad():
+            ref = O.cfm_sample(sd, cfg, cond=a['cond'], cond_mask=a['sample_cond_mask'], steps=3, method='rk4', y0=a['y0'])
+            ob = oracle_bf16(lambda: O.cfm_sample(sd, cfg, cond=a['cond'], cond_mask=a['sample_cond_mask'], steps=3, method='rk4',
+                                                  y0=a['y0']))
+        floor = 2e-2 * float(ref.abs().max())
+        assert maxerr(out, ref) <= max(1.5 * maxerr(ob, ref), floor), (maxerr(out, ref), maxerr(ob, ref))
+
+        w.odeint_kwargs['method'] = 'midpoint'
+        g = w.sample(cond=a['cond'], cond_mask=a['sample_cond_mask'], steps=9)
+        info = dict(vbx.ode.last_run_info)
+        assert info['graph'] and info['intervals'] == 8, info
+        os.environ['VBX_ODE_GRAPH'] = '0'
+        try:
+            e = w.sample(cond=a['cond'], cond_mask=a['sample_cond_mask'], steps=9)
+        finally:
+            del os.environ['VBX_ODE_GRAPH']
+        assert not vbx.ode.last_run_info['graph']
+        assert maxerr(g, e) <= 1e-2 * float(e.abs().max()), maxerr(g, e)
+        with torch.no_grad():
+            ref9 = O.cfm_sample(sd, cfg, cond=a['cond'], cond_mask=a['sample_cond_mask'], steps=9, method='midpoint', y0=a['y0'])
+        assert maxerr(g, ref9) <= 4e-2 * float(ref9.abs().max())
+    finally:
+        torch.randn_like = real

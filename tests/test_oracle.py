@@ -137,3 +137,25 @@ def test_fixed_grid_solver_known_answers(method):
     assert torch.equal(a, O.odeint_fixed_grid(lambda tt, y: y, y0, t, method=method))
     with pytest.raises(NotImplementedError):
         O.odeint_fixed_grid(lambda tt, y: y, y0, t, method='dopri5')
+
+
+def test_rk4_three_eighths_rule_known_answers():
+    """Fixed-grid 'rk4' as torchdiffeq implements it (RK4._step_func -> rk4_alt_step_func, the 3/8 rule; restated from the
+    published tableau, the package is absent: parity unpinned).  dy/dt = y has the classical 4th-order amplification factor
+    1 + h + h^2/2 + h^3/6 + h^4/24 for ANY 4-stage 4th-order rule; dy/dt = 4 t^3 pins the stage TIMES of the 3/8 rule
+    (t0, t0 + h/3, t0 + 2h/3, t1 with weights 1/8, 3/8, 3/8, 1/8) -- exact for cubics, and different from the classical rule's
+    midpoint stages on a quartic integrand, which the second check uses."""
+    t = torch.tensor([0., 0.1, 0.25, 0.45, 0.7, 1.0], dtype=torch.float64)
+    h = t[1:] - t[:-1]
+    y0 = torch.tensor([1.0, -2.0], dtype=torch.float64)
+    ys = O.odeint_fixed_grid(lambda tt, y: y, y0, t, method='rk4')
+    amp = 1 + h + h ** 2 / 2 + h ** 3 / 6 + h ** 4 / 24
+    want = torch.cat([torch.ones(1, dtype=torch.float64), torch.cumprod(amp, 0)])[:, None] * y0
+    assert torch.allclose(ys, want, rtol=1e-13, atol=0)
+    g = lambda s: 5 * s ** 4            # quartic integrand: the quadrature error separates the 3/8 rule from Simpson's rule
+    ys = O.odeint_fixed_grid(lambda tt, y: g(tt) * torch.ones_like(y), torch.zeros(1, dtype=torch.float64), t, method='rk4')
+    t0 = t[:-1]
+    quad = h * (g(t0) + 3 * g(t0 + h / 3) + 3 * g(t0 + 2 * h / 3) + g(t0 + h)) / 8
+    assert torch.allclose(ys[1:, 0], torch.cumsum(quad, 0), rtol=1e-13, atol=0)
+    simpson = h * (g(t0) + 4 * g(t0 + h / 2) + g(t0 + h)) / 6
+    assert not torch.allclose(ys[1:, 0], torch.cumsum(simpson, 0), rtol=1e-9, atol=0)

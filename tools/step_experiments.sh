@@ -8,7 +8,7 @@ OUT=gpurun_out/stepexp
 mkdir -p "$OUT"
 VBX_BATCHED_GB=1 timeout 300 python -m pytest tests/test_gpu_model.py -m gpu -x -q > "$OUT/tests_batched_gb.log" 2>&1
 tail -1 "$OUT/tests_batched_gb.log"
-VBX_EXPERIMENTAL_TESTS=1 timeout 200 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k flat_adam > "$OUT/tests_flat_adam.log" 2>&1
+timeout 200 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k flat_adam > "$OUT/tests_flat_adam.log" 2>&1
 tail -1 "$OUT/tests_flat_adam.log"
 timeout 240 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-sample > "$OUT/bench_base.json" 2> "$OUT/bench_base.err"
 VBX_BATCHED_GB=1 timeout 240 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-sample > "$OUT/bench_batched_gb.json" 2> "$OUT/bench_batched_gb.err"

@@ -21,7 +21,7 @@ from .modules import (  # noqa: F401
 )
 from .patch import patch_reference  # noqa: F401
 from .optim import FlatAdam  # noqa: F401
-from . import ops, _lib  # noqa: F401
+from . import ops, ode, modules, _lib  # noqa: F401
 
 __all__ = ['Transformer', 'VoiceBox', 'DurationPredictor', 'ConditionalFlowMatcherWrapper', 'AudioEncoderDecoder',
            'patch_reference']

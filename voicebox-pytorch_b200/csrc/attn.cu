@@ -1007,6 +1007,74 @@ extern "C" int vbx_debug_umma_bench(long long* out, int n, int a_mn, int b_mn, i
 #undef VBX_BENCH
   return (int)cudaGetLastError();
 }
+// ---- same measurement with SEVERAL issuing warps (each on its own accumulators): is the ~55 clk floor of N <= 64 MMAs a
+// property of the tensor pipe, or of one thread's issue path (ptxas wraps every tcgen05.mma in an ELECT / BRA.U.ANY loop)? ----
+namespace vbx {
+template <bool ATMEM>
+__global__ void __launch_bounds__(160, 1) umma_bench_mw_kernel(long long* out, int n, int a_mn, int b_mn, int iters, int nissuers) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 4 * kSubTileBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 4 * (int)kSubTileBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = *tmem_slot;
+  if (warp >= 1 && warp <= nissuers) {
+    const int w = warp - 1;
+    const uint32_t idesc = make_idesc(128, n, a_mn != 0, b_mn != 0);
+    const uint64_t a0 = a_mn ? sdesc_mn0(smem_u32(smem)) : sdesc_k0(smem_u32(smem));
+    const uint64_t b0 = b_mn ? sdesc_mn0(smem_u32(smem + 2 * kSubTileBytes)) : sdesc_k0(smem_u32(smem + 2 * kSubTileBytes));
+    const uint64_t as = a_mn ? koff_mn(1) : 2, bs = b_mn ? koff_mn(1) : 2;
+    const bool leader = (threadIdx.x & 31) == 0;
+    const uint32_t acc = tb + (uint32_t)w * 128;      // this warp's accumulator (n <= 128 columns); A-in-TMEM lives at col 448+
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (ATMEM) umma_bf16_ts(acc, tb + 448 + (k & 3) * 8, b0 + (k & 3) * bs, idesc, 1);
+          else umma_bf16(acc, a0 + (k & 3) * as, b0 + (k & 3) * bs, idesc, 1);
+        }
+      }
+      __syncwarp();
+    }
+    const long long t1 = clock64();
+    if (leader) umma_commit(&bars[w]);
+    mbar_wait(&bars[w], 0);
+    const long long t2 = clock64();
+    if (leader) {
+      out[2 * w] = t1 - t0;
+      out[2 * w + 1] = t2 - t0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+}  // namespace vbx
+extern "C" int vbx_debug_umma_bench_mw(long long* out, int n, int a_mn, int b_mn, int a_tmem, int iters, int ctas, int nissuers) {
+  const int smem = 4 * ptx::kSubTileBytes + 128;
+  if (nissuers < 1 || nissuers > 3 || n > 128) return VBX_E_SHAPE;   // 3 x 128 accumulator columns + 64 for the TMEM A operand
+  if (a_tmem) {
+    cudaFuncSetAttribute(vbx::umma_bench_mw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    vbx::umma_bench_mw_kernel<true><<<ctas, 160, smem>>>(out, n, a_mn, b_mn, iters, nissuers);
+  } else {
+    cudaFuncSetAttribute(vbx::umma_bench_mw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    vbx::umma_bench_mw_kernel<false><<<ctas, 160, smem>>>(out, n, a_mn, b_mn, iters, nissuers);
+  }
+  return (int)cudaGetLastError();
+}
 extern "C" int vbx_debug_set_trace(void* dev_ptr) {
   return (int)cudaMemcpyToSymbol(vbx::g_trace, &dev_ptr, sizeof(void*));
 }

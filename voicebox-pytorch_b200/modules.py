@@ -490,6 +490,28 @@ def _fix_times(times, batch):
     return times
 
 
+def _assemble_embedding(self, x, cond, cond_mask, cond_token_ids, drop, self_attn_mask):
+    """cat(x, [cond_emb], cond) in bf16 for the generic route (vp.py:1035-1076): conditioning masking, classifier-free drop
+    (`drop`: bool [B] or None -- rows whose conditioning becomes null_cond / the null token id, vp.py:1041-1054), token
+    embedding gather + interpolate_1d to the frame rate (vp.py:1058-1070)."""
+    seq_len = cond.shape[1]
+    cond = cond * ~cond_mask[..., None]
+    cond_ids = cond_token_ids
+    if exists(drop):
+        cond = torch.where(drop[:, None, None], self.null_cond, cond)
+        cond_ids = torch.where(drop[:, None], self.null_cond_id, cond_token_ids)
+    parts = [x]
+    if self.condition_on_text:
+        cond_emb = self.to_cond_emb(cond_ids)
+        if cond_emb.shape[-2] != seq_len:
+            cond_emb = interpolate_1d(cond_emb.transpose(1, 2), seq_len).transpose(1, 2)
+            if exists(self_attn_mask):
+                self_attn_mask = interpolate_1d(self_attn_mask, seq_len)
+        parts.append(cond_emb)
+    parts.append(cond)
+    return torch.cat(parts, dim=-1).to(BF16), self_attn_mask
+
+
 def voicebox_forward(self, x, *, times, cond_token_ids, self_attn_mask=None, cond_drop_prob=0.1, target=None, cond=None,
                      cond_mask=None):
     """VoiceBox.forward (vp.py:987-1115), same argument meaning and RNG draw order."""
@@ -514,22 +536,8 @@ def voicebox_forward(self, x, *, times, cond_token_ids, self_attn_mask=None, con
     if not self.condition_on_text and not cond_drop_prob > 0. and not upstream_grad:
         emb = ops.embed_concat(x, cond, cond_mask)            # cond * ~mask, cat, bf16 cast: one pass
     else:
-        cond = cond * ~cond_mask[..., None]
-        cond_ids = cond_token_ids
-        if cond_drop_prob > 0.:
-            drop = prob_mask_like(cond.shape[:1], cond_drop_prob, self.device)
-            cond = torch.where(drop[:, None, None], self.null_cond, cond)
-            cond_ids = torch.where(drop[:, None], self.null_cond_id, cond_token_ids)
-        parts = [x]
-        if self.condition_on_text:
-            cond_emb = self.to_cond_emb(cond_ids)
-            if cond_emb.shape[-2] != seq_len:
-                cond_emb = interpolate_1d(cond_emb.transpose(1, 2), seq_len).transpose(1, 2)
-                if exists(self_attn_mask):
-                    self_attn_mask = interpolate_1d(self_attn_mask, seq_len)
-            parts.append(cond_emb)
-        parts.append(cond)
-        emb = torch.cat(parts, dim=-1).to(BF16)
+        drop = prob_mask_like(cond.shape[:1], cond_drop_prob, self.device) if cond_drop_prob > 0. else None
+        emb, self_attn_mask = _assemble_embedding(self, x, cond, cond_mask, cond_token_ids, drop, self_attn_mask)
 
     pred = _voicebox_body(self, emb, times, self_attn_mask)
     if not exists(target):
@@ -538,12 +546,41 @@ def voicebox_forward(self, x, *, times, cond_token_ids, self_attn_mask=None, con
     return ops.masked_mse(pred, loss_mask, target=target)
 
 
+CFG_BATCHED = os.environ.get('VBX_CFG_BATCHED', '1') != '0'
+
+
+def _cfg_batched(self, x, *, times, cond_token_ids, cond, cond_mask=None, self_attn_mask=None, cond_scale=1.):
+    """Classifier-free guidance as ONE forward over a 2B batch: rows [0, B) conditioned, rows [B, 2B) with null conditioning
+    (what the reference computes in two sequential passes at cond_drop_prob 0 and 1, vp.py:972-985; at p = 1 `prob_mask_like`
+    draws nothing, so there is no RNG order to preserve).  Samples are independent through the whole trunk, so the halves
+    equal the two separate passes up to GEMM tile selection; every weight is read once instead of twice per evaluation."""
+    x = self.proj_in(x)
+    cond = self.proj_in(cond)
+    B, seq_len, _ = cond.shape
+    times = _fix_times(times, B)
+    if not exists(cond_mask):
+        cond_mask = torch.ones((B, seq_len), device=cond.device, dtype=torch.bool)
+    drop = torch.zeros((2 * B,), device=cond.device, dtype=torch.bool)
+    drop[B:] = True
+    two = lambda t: None if t is None else torch.cat((t, t), dim=0)
+    emb, mask2 = _assemble_embedding(self, two(x), two(cond), two(cond_mask), two(cond_token_ids), drop, two(self_attn_mask))
+    pred = _voicebox_body(self, emb, two(times), mask2).to(x.dtype)
+    logits, null_logits = pred[:B], pred[B:]
+    return null_logits + (logits - null_logits) * cond_scale
+
+
 @torch.inference_mode()
 def voicebox_forward_with_cond_scale(self, *args, cond_scale=1., **kwargs):
     """vp.py:972-985."""
-    logits = self.forward(*args, cond_drop_prob=0., **kwargs)
     if cond_scale == 1.:
-        return logits
+        return self.forward(*args, cond_drop_prob=0., **kwargs)
+    simple = (len(args) == 1 and kwargs.get('target') is None and kwargs.get('cond') is not None
+              and (kwargs.get('cond_mask') is not None or not self.training)
+              and set(kwargs) <= {'times', 'cond_token_ids', 'cond', 'cond_mask', 'self_attn_mask', 'target'})
+    if CFG_BATCHED and simple:
+        kw = {k: v for k, v in kwargs.items() if k != 'target'}
+        return _cfg_batched(self, args[0], cond_scale=cond_scale, **kw)
+    logits = self.forward(*args, cond_drop_prob=0., **kwargs)
     null_logits = self.forward(*args, cond_drop_prob=1., **kwargs)
     return null_logits + (logits - null_logits) * cond_scale
 

@@ -9,11 +9,17 @@ rewrites the x-half of the next evaluation's bf16 `to_embed` input and the midpo
 (no host round trip per step; the loop is CUDA-graph capturable).  The conditioning half of that input
 (cond * ~cond_mask, vp.py:1035) is constant over the trajectory and is written once.
 """
+import os
+
 import torch
 
 from . import ops
 
-METHODS = ('euler', 'midpoint')
+METHODS = ('euler', 'midpoint', 'rk4')
+# one solver step (1 or 2 evaluations + stage combines) is captured ONCE as a CUDA graph and replayed per interval when the
+# trajectory has at least this many intervals (capture costs about one eager step); VBX_ODE_GRAPH=0 disables it
+GRAPH_MIN_INTERVALS = int(os.environ.get('VBX_ODE_GRAPH_MIN', 4))
+last_run_info = {}   # {'graph': bool, 'intervals': int, 'why': str}: what the last odeint_fixed call did (read by bench.py)
 
 
 def odeint_fixed(vb, *, cond, cond_mask=None, cond_token_ids=None, self_attn_mask=None, steps=3, cond_scale=1.,
@@ -25,6 +31,36 @@ def odeint_fixed(vb, *, cond, cond_mask=None, cond_token_ids=None, self_attn_mas
     y = torch.randn_like(cond)                             # vp.py:1289
     t = torch.linspace(0, 1, steps, device=device)        # vp.py:1290
     fast = (not vb.condition_on_text) and cond_scale == 1. and isinstance(vb.proj_in, torch.nn.Identity)
+
+    if method == 'rk4':
+        # torchdiffeq's fixed-grid 'rk4' is the 3/8-rule variant (rk4_alt_step_func; restated, the package is absent: parity
+        # unpinned, see oracle/voicebox_oracle.py:odeint_fixed_grid).  4 evaluations per interval; the stage combines are
+        # plain fp32 torch ops on y (5 passes of 4 B/elem per interval against 4 x 27 TFLOP of evaluations).
+        y = y.float().contiguous()
+        if fast:
+            if not exists(cond_mask):
+                cond_mask = torch.ones((B, N), device=device, dtype=torch.bool)
+            emb = torch.empty((B, N, 2 * D), device=device, dtype=torch.bfloat16)
+            ops.embed_concat(y, cond, cond_mask, out=emb)
+
+            def f(tt, yy):
+                ops.embed_concat(yy.contiguous(), None, cond_mask, out=emb)   # refresh the x-half only
+                return _voicebox_body(vb, emb, tt, self_attn_mask).float()
+        else:
+            def f(tt, yy):
+                return vb.forward_with_cond_scale(yy, times=tt, cond_token_ids=cond_token_ids, cond=cond, cond_scale=cond_scale,
+                                                  cond_mask=cond_mask, self_attn_mask=self_attn_mask).float()
+        for i in range(steps - 1):
+            t0, t1 = t[i], t[i + 1]
+            dt = t1 - t0
+            k1 = f(t0, y)
+            k2 = f(t0 + dt / 3, y + dt * k1 / 3)
+            k3 = f(t0 + dt * 2 / 3, y + dt * (k2 - k1 / 3))
+            k4 = f(t1, y + dt * (k1 - k2 + k3))
+            y = y + dt * (k1 + 3 * (k2 + k3) + k4) / 8
+        last_run_info.clear()
+        last_run_info.update(graph=False, intervals=steps - 1, why='rk4: eager')
+        return y
 
     if not fast:
         # generic path (text conditioning / classifier-free guidance): the reference's own control flow on the public API
@@ -42,19 +78,65 @@ def odeint_fixed(vb, *, cond, cond_mask=None, cond_token_ids=None, self_attn_mas
                 ops.ode_axpy(y, f1.to(torch.bfloat16), t, i, i + 1, half=False, y_out=y)
         return y
 
-    y = y.float().contiguous()
+    y0 = y.float()
     if not exists(cond_mask):  # eval default: conditioning fully masked (vp.py:1028-1030)
         cond_mask = torch.ones((B, N), device=device, dtype=torch.bool)
-    emb = torch.empty((B, N, 2 * D), device=device, dtype=torch.bfloat16)
+    intervals = steps - 1
+    use_graph = os.environ.get('VBX_ODE_GRAPH', '1') != '0' and intervals >= GRAPH_MIN_INTERVALS
+    why = 'ok' if use_graph else ('disabled (VBX_ODE_GRAPH=0)' if intervals >= GRAPH_MIN_INTERVALS
+                                  else f'fewer than {GRAPH_MIN_INTERVALS} intervals')
+
+    # Working set of one trajectory, at FIXED addresses so that one solver step can be captured as a CUDA graph and replayed:
+    #   y (fp32 state), emb (bf16 to_embed input: [x | cond * ~mask]), y_mid / t_mid (midpoint stage), and tw = the 2-element
+    #   DEVICE window [t0, t1] the stage combines read their interval from (refreshed by an 8-byte device copy per interval).
+    # The captured step is kept on the VoiceBox object and reused by later sample() calls of the same geometry as long as no
+    # parameter changed (the graph holds the addresses of the cached bf16 weight copies).
+    sig = (B, N, D, method, str(device), tuple((p._version, p.data_ptr()) for p in vb.parameters()))
+    st = vb.__dict__.get('_vbx_ode_state') if use_graph and self_attn_mask is None else None
+    if st is None or st['sig'] != sig:
+        st = dict(sig=sig, graph=None,
+                  y=torch.empty((B, N, D), device=device, dtype=torch.float32),
+                  emb=torch.empty((B, N, 2 * D), device=device, dtype=torch.bfloat16),
+                  y_mid=torch.empty((B, N, D), device=device, dtype=torch.float32) if method == 'midpoint' else None,
+                  t_mid=torch.empty((1,), device=device, dtype=torch.float32),
+                  tw=torch.empty((2,), device=device, dtype=torch.float32))
+    y, emb, y_mid, t_mid, tw = st['y'], st['emb'], st['y_mid'], st['t_mid'], st['tw']
+    y.copy_(y0)
     ops.embed_concat(y, cond, cond_mask, out=emb)
-    y_mid = torch.empty_like(y) if method == 'midpoint' else None
-    t_mid = torch.empty((1,), device=device, dtype=torch.float32)
-    for i in range(steps - 1):
-        f0 = _voicebox_body(vb, emb, t[i], self_attn_mask)
+
+    def one_step():
+        f0 = _voicebox_body(vb, emb, tw[0], self_attn_mask)
         if method == 'euler':
-            ops.ode_axpy(y, f0, t, i, i + 1, half=False, y_out=y, emb=emb)
+            ops.ode_axpy(y, f0, tw, 0, 1, half=False, y_out=y, emb=emb)
         else:
-            ops.ode_axpy(y, f0, t, i, i + 1, half=True, y_out=y_mid, emb=emb, t_out=t_mid)
+            ops.ode_axpy(y, f0, tw, 0, 1, half=True, y_out=y_mid, emb=emb, t_out=t_mid)
             f1 = _voicebox_body(vb, emb, t_mid[0], self_attn_mask)
-            ops.ode_axpy(y, f1, t, i, i + 1, half=False, y_out=y, emb=emb)
-    return y
+            ops.ode_axpy(y, f1, tw, 0, 1, half=False, y_out=y, emb=emb)
+
+    first = 0
+    if use_graph and st['graph'] is None:
+        # interval 0 runs eagerly: it is the warm-up every capture needs (bf16 weight copies, rotary tables, cuBLASLt
+        # workspaces and kernel attributes are set up outside the capture) -- and it is real work, not a dry run
+        tw.copy_(t[0:2])
+        one_step()
+        first = 1
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                one_step()              # captured, not executed
+            st['graph'] = g
+            if self_attn_mask is None:
+                vb.__dict__['_vbx_ode_state'] = st
+        except Exception as ex:         # nothing ran during a failed capture: fall back to eager launches
+            why = f'capture failed: {ex!r}'
+            torch.cuda.synchronize()
+    graph = st['graph'] if use_graph else None
+    for i in range(first, intervals):
+        tw.copy_(t[i:i + 2])
+        if graph is not None:
+            graph.replay()
+        else:
+            one_step()
+    last_run_info.clear()
+    last_run_info.update(graph=graph is not None, intervals=intervals, why=why)
+    return y.clone() if graph is not None else y   # the graph's state buffer is reused by the next call
