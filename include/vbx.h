@@ -121,6 +121,30 @@ int vbx_ode_axpy(const float* y, const uint16_t* f, const float* t, int64_t i0, 
                  uint16_t* emb, float* t_out, int64_t B, int64_t N, int64_t D, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * bf16 GEMM on tcgen05 tensor cores with fused epilogues          replaces F.linear under autocast (vp.py:320, 333, 348, 1078, 1092)
+ *                                                                 and, for vbx_ff1_geglu, vp.py:337-346: Linear(D, 2F) + GEGLU.
+ * a: bf16 [M, K] activations; w: bf16 [N, K] (nn.Linear layout, K contiguous); bias: bf16 [N] or NULL; c: bf16 [M, N].
+ * fp32 accumulation in tensor memory, one rounding to bf16 on output.  K % 8 == 0, N % 8 == 0, N >= 32; any M. */
+int vbx_gemm_bf16(const uint16_t* a, const uint16_t* w, const uint16_t* bias, uint16_t* c, int64_t M, int64_t N, int64_t K,
+                  void* stream);
+/* x: bf16 [M, K]; w1: bf16 [2Fp, K] = (value rows | gate rows), b1: bf16 [2Fp] (the zero-padded operand layout, Fp % 32 == 0);
+ *   h = x w1^T + b1 (rounded to bf16, as the reference's autocast Linear output), g = gelu_erf(h[:, Fp:]) * h[:, :Fp]
+ * h: bf16 [M, 2Fp] or NULL (inference: the intermediate is never written); g: bf16 [M, Fp]. */
+int vbx_ff1_geglu(const uint16_t* x, const uint16_t* w1, const uint16_t* b1, uint16_t* h, uint16_t* g, int64_t M, int64_t Fp,
+                  int64_t K, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Operand packing                                               replaces the per-use fp32 -> bf16 casts of every Linear weight
+ *                                                               and bias under autocast (trainer.py:267; vp.py:259-260, 320,
+ *                                                               333, 345, 348) -- ~14 cast kernels per layer per forward --
+ *                                                               and the GEGLU zero-padding copies, with ONE launch.
+ * segs: DEVICE table, n_seg entries of 6 x int64: { src (const float*), dst (uint16_t*), rows, cols, src_pitch, dst_pitch }
+ * (pitches in elements); row_start: DEVICE int64 [n_seg+1], exclusive prefix sum of `rows`; total_rows = row_start[n_seg].
+ * Every segment copies a [rows x cols] fp32 matrix into a bf16 matrix of a possibly larger pitch; bytes outside the copied
+ * columns / rows are never written (operand buffers are allocated zero-filled once, which is what makes the padding exact). */
+int vbx_pack_bf16(const void* segs, const int64_t* row_start, int64_t n_seg, int64_t total_rows, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Fused gradient clip + Adam step over FLAT buffers              replaces accelerator.clip_grad_norm_ + optim.step()
  *                                                                 (trainer.py:274-278; optimizer.py:32-35: torch Adam,
  *                                                                 betas (0.9, 0.99), eps 1e-8; AdamW when wd > 0)

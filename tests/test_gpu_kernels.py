@@ -369,3 +369,41 @@ def test_flat_adam_matches_torch_adam(vbx, clip):
     opt.found_inf = torch.ones(1, device='cuda')                         # skipped step: nothing may change
     opt.step()
     assert torch.equal(opt.flat_p, before)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('M,K,N,with_bias', [(300, 128, 256, True), (128, 64, 64, False), (1040 * 2, 1024, 3072, False),
+                                             (777, 2752, 1024, True), (4096, 1024, 1000, True)])
+def test_tcgen05_gemm_plain_vs_fp32(vbx, M, K, N, with_bias):
+    """csrc/gemm.cu, mode PLAIN: C = A W^T + b with fp32 accumulation in tensor memory and ONE rounding to bf16 -- against the
+    fp32 product of the same bf16 operands: 2^-8 relative to the output max plus the fp32 accumulation-order noise.  Covers
+    row tails (M % 128), column tails (N % 256, N % 64), K tails (K % 64) and a single-tile problem."""
+    torch.manual_seed(11)
+    a = torch.randn(M, K, device='cuda').to(BF16)
+    w = (torch.randn(N, K, device='cuda') / math.sqrt(K)).to(BF16)
+    b = torch.randn(N, device='cuda').to(BF16) if with_bias else None
+    c = vbx.ops.gemm_bf16(a, w, b)
+    ref = a.float() @ w.float().t() + (b.float() if with_bias else 0)
+    assert c.shape == (M, N) and c.dtype == BF16
+    assert rel_err(c, ref) < 2 ** -7
+
+
+@pytest.mark.parametrize('T,K,Fp', [(300, 128, 192), (520, 128, 384), (1040 * 2, 1024, 2752), (129, 64, 32)])
+def test_tcgen05_ff1_geglu_fused_epilogue(vbx, T, K, Fp):
+    """csrc/gemm.cu, GEGLU modes (vp.py:337-346): h = x W1^T + b1 rounded to bf16, g = gelu_erf(gate) * value on the ROUNDED h --
+    the fused kernel must reproduce cuBLASLt GEMM + vbx_geglu_fwd: h to one bf16 ulp of the accumulation-order noise, g = the
+    GEGLU of ITS OWN h (checked by re-running the stand-alone GEGLU kernel on it), and the no-h inference variant the same g."""
+    torch.manual_seed(12)
+    x = torch.randn(T, K, device='cuda').to(BF16)
+    w1 = (torch.randn(2 * Fp, K, device='cuda') / math.sqrt(K)).to(BF16)
+    b1 = (0.1 * torch.randn(2 * Fp, device='cuda')).to(BF16)
+    h, g = vbx.ops.ff1_geglu(x, w1, b1, True)
+    h_ref = x.float() @ w1.float().t() + b1.float()
+    assert rel_err(h, h_ref) < 2 ** -7
+    with torch.no_grad():
+        g_from_h = vbx.ops.geglu(h)
+    assert rel_err(g, g_from_h) <= 2 ** -8          # same formula on the same rounded h (at most an ulp from FMA contraction)
+    _, g2 = vbx.ops.ff1_geglu(x, w1, b1, False)
+    assert torch.equal(g2, g)
+    val, gate = rbf(h_ref).chunk(2, dim=-1)
+    assert rel_err(g, torch.nn.functional.gelu(gate) * val) < 2 ** -6

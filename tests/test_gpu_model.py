@@ -339,3 +339,66 @@ def test_sampling_rk4_and_graph_replay_vs_oracle(vbx):
         assert maxerr(g, ref9) <= 4e-2 * float(ref9.abs().max())
     finally:
         torch.randn_like = real
+
+
+def test_operand_pack_matches_per_use_casts_and_routes_fp32_gradients(vbx):
+    """pack.py: (a) one vbx_pack_bf16 launch reproduces every per-use cast / GEGLU zero-padding / gamma-beta stacking bit for
+    bit; (b) a training step on the packed path gives the same loss as the per-use-cast path (identical bf16 operands, identical
+    kernels) and the same gradients up to the bf16 rounding the packed path REMOVES from the weight gradients; (c) gradients
+    land in the flat bucket in place, and a second step after an optimizer update sees the refreshed operands."""
+    from voicebox_pytorch_b200 import pack as P
+    from voicebox_pytorch_b200.dist import FlatGradBucket
+    a, sd, w, cfg = build(vbx, 'voicebox_d128_l2_h4_n200')          # F = int(128*8/3) = 341 -> Fp = 384: padded operands
+    vb = w.voicebox
+    pk = P.for_module(vb, vbx.modules._build_pack(vb))
+    assert pk.refresh() and not pk.refresh()                         # second call: nothing changed, no launch
+    ff = vb.transformer.layers[1][5]
+    f, fp = 341, 384
+    e1, eb1, e2 = pk.lookup(ff[0].weight), pk.lookup(ff[0].bias), pk.lookup(ff[3].weight)
+    w1 = ff[0].weight.detach().to(torch.bfloat16)
+    assert e1.op.shape == (2 * fp, 128) and torch.equal(e1.op[:f], w1[:f]) and torch.equal(e1.op[fp:fp + f], w1[f:])
+    assert float(e1.op[f:fp].abs().max()) == 0 and float(e1.op[fp + f:].abs().max()) == 0
+    b1 = ff[0].bias.detach().to(torch.bfloat16)
+    assert torch.equal(eb1.op[:f], b1[:f]) and torch.equal(eb1.op[fp:fp + f], b1[f:]) and float(eb1.op[f:fp].abs().max()) == 0
+    assert e2.op.shape == (128, fp) and torch.equal(e2.op[:, :f], ff[3].weight.detach().to(torch.bfloat16))
+    assert float(e2.op[:, f:].abs().max()) == 0
+    W, bvec, _ = vb.transformer.__dict__['_vbx_gb_stack']
+    norms = [n for layer in vb.transformer.layers for n in (layer[2], layer[4])]
+    for i, n in enumerate(norms):
+        assert torch.equal(W[2 * i], n.to_gamma.weight.detach().to(torch.bfloat16))
+        assert torch.equal(W[2 * i + 1], n.to_beta.weight.detach().to(torch.bfloat16))
+        assert torch.equal(bvec[2 * i], n.to_gamma.bias.detach().to(torch.bfloat16))
+    assert torch.equal(pk.lookup(vb.to_pred.weight).op, vb.to_pred.weight.detach().to(torch.bfloat16))
+
+    def step(packed, bucketed):
+        vbx.modules.PACKED = packed
+        try:
+            w.zero_grad(set_to_none=True)
+            bucket = FlatGradBucket(w) if bucketed else None
+            vb.train()
+            loss = vbx.modules.voicebox_cfm_loss(vb, a['x0'], a['x1'], a['times'], sigma=float(a['sigma']), cond_mask=a['cond_mask'])
+            loss.backward()
+            return float(loss), {n: p.grad.clone() for n, p in vb.named_parameters() if p.grad is not None}, bucket
+        finally:
+            vbx.modules.PACKED = True
+    l0, g0, _ = step(False, False)
+    l1, g1, _ = step(True, False)
+    l2, g2, bucket = step(True, True)
+    # same bf16 operands; only the 8 gamma/beta projections differ in GEMM algorithm (batched vs one by one): <= one bf16 ulp on
+    # a few gamma/beta entries
+    assert l1 == l2 and abs(l0 - l1) <= 2e-4 * abs(l0), (l0, l1, l2)
+    assert set(g0) == set(g1) == set(g2)
+    for n in g0:
+        scale = float(g0[n].abs().max()) + 1e-12
+        assert maxerr(g1[n], g0[n]) <= 1e-2 * scale, (n, maxerr(g1[n], g0[n]), scale)     # bf16 rounding of dW removed
+        assert maxerr(g2[n], g1[n]) <= 1e-5 * scale, (n, maxerr(g2[n], g1[n]), scale)     # in-place accumulation == returned
+    for p in bucket.params:
+        assert p.grad.data_ptr() == bucket.flat.data_ptr() + 4 * bucket.offsets[bucket.params.index(p)]
+    # an optimizer update bumps the version counters: the next forward re-packs and the loss changes accordingly
+    with torch.no_grad():
+        for p in vb.parameters():
+            if p.requires_grad:
+                p.add_(0.01 * torch.randn_like(p))
+    l3, _, _ = step(True, False)
+    l4, _, _ = step(False, False)
+    assert abs(l3 - l4) <= 2e-4 * abs(l4) and abs(l3 - l1) > 1e-3 * abs(l1), (l1, l3, l4)

@@ -32,6 +32,9 @@ _SIGNATURES = {
     'vbx_attn_bwd': [_vp, _vp, _vp, _i64, _i64, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64,
                      _vp],
     'vbx_adam_step': [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _int, _i64, _vp, _vp, _vp],
+    'vbx_pack_bf16': [_vp, _vp, _i64, _i64, _vp],
+    'vbx_gemm_bf16': [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
+    'vbx_ff1_geglu': [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
     'vbx_umma_selftest': [_vp, _vp, _vp, _int, _vp],
 }
 

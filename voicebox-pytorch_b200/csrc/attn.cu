@@ -880,6 +880,21 @@ static int make_tmap(CUtensorMap* out, const void* base, int64_t inner, int64_t 
   return rc == CUDA_SUCCESS ? VBX_OK : VBX_E_DRIVER;
 }
 
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t inner, int64_t rows, int64_t row_pitch, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return VBX_E_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (row_pitch * 2) % 16 || inner <= 0 || rows <= 0 || box_rows <= 0 || box_rows > 256)
+    return VBX_E_ALIGN;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)row_pitch * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS ? VBX_OK : VBX_E_DRIVER;
+}
+
 int make_tmap_bf16_4d(CUtensorMap* out, const void* base, int64_t N, int64_t H, int64_t B, int64_t n_stride, int64_t h_stride,
                       int64_t b_stride, int box_rows) {
   return make_tmap(out, base, kDh, N, H, B, n_stride, h_stride, b_stride, box_rows);

@@ -14,6 +14,6 @@ TAG="${OUT%.so}"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v "${DEFS[@]}" \
   -c "$HERE/attn.cu" -o "$HERE/../build/attn_$TAG.o" 2> "$HERE/../build/attn_$TAG.ptxas.log" || { cat "$HERE/../build/attn_$TAG.ptxas.log"; exit 1; }
 OBJS=()
-for f in api norm_ffn cfm_ode convpos qkrope optim; do OBJS+=("$HERE/../build/$f.o"); done
+for f in api norm_ffn cfm_ode convpos qkrope optim pack gemm; do OBJS+=("$HERE/../build/$f.o"); done
 "$NVCC" -shared -o "$HERE/../lib/$OUT" "${OBJS[@]}" "$HERE/../build/attn_$TAG.o" -lcudart
 echo "built $HERE/../lib/$OUT (${DEFS[*]})"

@@ -1,0 +1,311 @@
+// bf16 GEMM on tcgen05 tensor cores with fused epilogues (sm_100a):  C[M, N] = A[M, K] W[N, K]^T (+ bias), both operands
+// K-major (activations [tokens, features] and nn.Linear weights [out, in] as they lie in memory).
+//
+//   mode PLAIN      C = A W^T + b                       -> bf16 [M, N]                          (vp.py:320, 333, 348, 1078, 1092)
+//   mode GEGLU      h = A W1^T + b1 ; g = gelu_erf(h[:, Fp:]) * h[:, :Fp]   -> h bf16 [M, 2Fp] (saved for the backward), g bf16 [M, Fp]
+//   mode GEGLU_NOH  same, h never written (inference: no backward)                               (vp.py:337-346)
+// The GEGLU modes replace the Linear(D, 2F) GEMM *and* the GEGLU pass over its output: the (value | gate) pair of every output
+// column lands in the same accumulator tile (columns [0,128) = value rows j0.. of W1, columns [128,256) = gate rows Fp + j0..),
+// so bias, rounding to bf16 (the reference's autocast output dtype), exact-erf GELU and the product happen on the accumulator
+// before anything is written: the 2Fp-wide intermediate is written once (training) or not at all (inference) and never re-read.
+//
+// Persistent, warp-specialised CTA (one per SM, 192 threads), tile 128 x 256 x 64, 4-stage TMA ring (48 KB per stage):
+//   warp 0     TMA producer: A box {64, 128} + two W boxes {64, 128} per stage, SWIZZLE_128B (= the canonical K-major UMMA layout)
+//   warp 1     TMEM allocator (all 512 columns: two 256-column fp32 accumulators) + tcgen05.mma issuer (M = 128, N = 256, K = 16)
+//   warps 2-5  epilogue: tcgen05.ld the accumulator (one row per thread), bias / GELU in registers, bf16 tiles staged through a
+//              private 4 KB shared-memory slice per warp in the SWIZZLE_128B pattern and written with TMA stores (clipped at the
+//              tensor edges by the tensor map), overlapped with the next tile's main loop through the second accumulator.
+#include "umma.cuh"
+
+namespace vbx {
+using namespace ptx;
+
+namespace gemm {
+constexpr int kBM = 128, kBN = 256, kBK = 64, kStages = 4;
+constexpr uint32_t kABytes = kBM * kBK * 2, kBBytes = kBN * kBK * 2, kStageBytes = kABytes + kBBytes;   // 16 + 32 KB
+constexpr uint32_t kOffOut = kStages * kStageBytes;                 // 2 x [128 rows][64 bf16] output staging blocks
+constexpr uint32_t kOutBlockBytes = kBM * 64 * 2;
+constexpr uint32_t kOffBar = kOffOut + 2 * kOutBlockBytes;
+enum { FULL = 0, EMPTY = kStages, TFULL = 2 * kStages, TEMPTY = 2 * kStages + 2, NUM_BARS = 2 * kStages + 4 };
+constexpr uint32_t kSmemBytes = kOffBar + NUM_BARS * 8 + 16;
+static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB)");
+constexpr int kThreads = 192;
+enum Mode { PLAIN = 0, GEGLU = 1, GEGLU_NOH = 2 };
+}  // namespace gemm
+
+VBX_DEVINL void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+VBX_DEVINL void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+VBX_DEVINL void tma_wait_group_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+// 32 packed bf16 pairs (64 columns of this thread's row) -> this warp's [32 rows][128 B] SWIZZLE_128B slice -> one TMA store.
+// `slice` alternates between the two staging blocks: before it is overwritten, the store issued two blocks ago (the last one
+// that read it) must have finished reading -- at most ONE younger bulk group may still be pending.
+VBX_DEVINL void store_block(uint8_t* slice, const uint32_t (&pk)[32], const CUtensorMap* map, int col, int row, int lane) {
+  if (lane == 0) tma_wait_group_read1();
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<uint4*>(slice + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(map, slice, col, row);
+    tma_commit_group();
+  }
+}
+
+VBX_DEVINL uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = f2bf(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// bias[col .. col+32) (bf16) -> fp32; all threads of the CTA read the same addresses (L1 broadcast)
+VBX_DEVINL void load_bias32(const uint16_t* bias, int col, float (&b)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float t[8];
+    unpack8(*reinterpret_cast<const uint4*>(bias + col + 8 * i), t);
+#pragma unroll
+    for (int x = 0; x < 8; ++x) b[8 * i + x] = t[x];
+  }
+}
+
+// mA: A [M, K]; mW: W [N_total, K] (box 128 rows); output maps (box {64, 32}): PLAIN: mO0 = C.  GEGLU: mO0 = value half of h,
+// mO1 = gate half of h, mO2 = g.  n_tiles = column tiles (PLAIN: ceil(N / 256); GEGLU: ceil(Fp / 128)).  gate_row0: row of W
+// where the second 128-row box of a tile starts, relative to the first: PLAIN 128, GEGLU Fp.
+template <int MODE>
+__global__ void __launch_bounds__(gemm::kThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW, const __grid_constant__ CUtensorMap mO0,
+                 const __grid_constant__ CUtensorMap mO1, const __grid_constant__ CUtensorMap mO2, const uint16_t* __restrict__ bias,
+                 int M, int n_cols, int K, int m_tiles, int n_tiles, int second_box_row) {
+  using namespace gemm;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + NUM_BARS * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (K + kBK - 1) / kBK;
+  const int ntiles = m_tiles * n_tiles;
+  constexpr int kColsPerTile = (MODE == PLAIN) ? 256 : 128;   // output columns a tile advances by
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&bars[FULL + s], 1);
+      mbar_init(&bars[EMPTY + s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&bars[TFULL + a], 1);
+      mbar_init(&bars[TEMPTY + a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mA);
+    tma_prefetch_desc(&mW);
+    tma_prefetch_desc(&mO0);
+    if (MODE == GEGLU) tma_prefetch_desc(&mO1);
+    if (MODE != PLAIN) tma_prefetch_desc(&mO2);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer ------------------------------------------------
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * kBM, j0 = (tile % n_tiles) * kColsPerTile;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kStages;
+          mbar_wait(&bars[EMPTY + s], ((it / kStages) & 1) ^ 1);
+          uint8_t* st = smem + s * kStageBytes;
+          mbar_arrive_expect_tx(&bars[FULL + s], kStageBytes);
+          tma_load_2d(st, &mA, &bars[FULL + s], kb * kBK, m0);
+          tma_load_2d(st + kABytes, &mW, &bars[FULL + s], kb * kBK, j0);
+          tma_load_2d(st + kABytes + kBBytes / 2, &mW, &bars[FULL + s], kb * kBK, second_box_row + j0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer --------------------------------------------------
+    constexpr uint32_t idesc = make_idesc(kBM, kBN, false, false);
+    const uint64_t dA0 = sdesc_k0(smem_u32(smem)), dB0 = sdesc_k0(smem_u32(smem + kABytes));
+    const bool leader = lane == 0;
+    int it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const int acc = tcount & 1;
+      mbar_wait(&bars[TEMPTY + acc], ((tcount >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * kBN;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % kStages;
+        mbar_wait(&bars[FULL + s], (it / kStages) & 1);
+        tc_fence_after();
+        if (leader) {
+          const uint64_t so = (uint64_t)s * (kStageBytes >> 4);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) umma_bf16(d_tmem, dA0 + so + koff_k(k), dB0 + so + koff_k(k), idesc, (kb | k) != 0);
+          umma_commit(&bars[EMPTY + s]);
+          if (kb == nkb - 1) umma_commit(&bars[TFULL + acc]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue ----------------------------------------------------
+    const int q = warp & 3;                                   // TMEM lane quarter this warp may access
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint8_t* slice0 = smem + kOffOut + q * 4096;
+    uint8_t* slice1 = slice0 + kOutBlockBytes;
+    int tcount = 0, blk = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const int acc = tcount & 1;
+      const int m0 = (tile / n_tiles) * kBM, j0 = (tile % n_tiles) * kColsPerTile;
+      const int row = m0 + q * 32;
+      mbar_wait(&bars[TFULL + acc], (tcount >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_acc = t_lane + (uint32_t)acc * kBN;
+      if (MODE == PLAIN) {
+#pragma unroll 1
+        for (int jj = 0; jj < 4; ++jj) {                       // 64 output columns per block
+          uint32_t pk[32];
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            float v[32], b[32];
+            tmem_ld32(t_acc + jj * 64 + hf * 32, v);
+            if (jj == 3 && hf == 1) {                          // last read of this accumulator: hand it back to the MMA warp
+              tc_fence_before();
+              mbar_arrive(&bars[TEMPTY + acc]);
+            }
+            if (bias != nullptr) {
+              const int col = min(j0 + jj * 64 + hf * 32, n_cols - 32);   // clipped columns are discarded by the store
+              load_bias32(bias, col, b);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += b[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[hf * 16 + i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          }
+          store_block((blk & 1) ? slice1 : slice0, pk, &mO0, j0 + jj * 64, row, lane);
+          ++blk;
+        }
+      } else {
+#pragma unroll 1
+        for (int jj = 0; jj < 2; ++jj) {                       // value columns [64jj, +64) with gate columns [128 + 64jj, +64)
+          uint32_t hv[32], hg[32], gg[32];
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            float v[32], g[32], b[32];
+            tmem_ld32(t_acc + jj * 64 + hf * 32, v);
+            tmem_ld32(t_acc + 128 + jj * 64 + hf * 32, g);
+            if (jj == 1 && hf == 1) {
+              tc_fence_before();
+              mbar_arrive(&bars[TEMPTY + acc]);
+            }
+            const int col = min(j0 + jj * 64 + hf * 32, n_cols - 32);     // n_cols = Fp here
+            load_bias32(bias, col, b);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += b[i];
+            load_bias32(bias, n_cols + col, b);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) g[i] += b[i];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              // h is a bf16 tensor in the reference (autocast output of the Linear): GEGLU sees the ROUNDED value and gate
+              const __nv_bfloat162 v2 = f2bf(v[2 * i], v[2 * i + 1]), g2 = f2bf(g[2 * i], g[2 * i + 1]);
+              const float2 vf = bf2f(v2), gf = bf2f(g2);
+              hv[hf * 16 + i] = *reinterpret_cast<const uint32_t*>(&v2);
+              hg[hf * 16 + i] = *reinterpret_cast<const uint32_t*>(&g2);
+              gg[hf * 16 + i] = pack_bf16x2(gelu_f(gf.x) * vf.x, gelu_f(gf.y) * vf.y);
+            }
+          }
+          const int col = j0 + jj * 64;
+          if (MODE == GEGLU) {
+            store_block((blk & 1) ? slice1 : slice0, hv, &mO0, col, row, lane);
+            ++blk;
+            store_block((blk & 1) ? slice1 : slice0, hg, &mO1, col, row, lane);
+            ++blk;
+          }
+          store_block((blk & 1) ? slice1 : slice0, gg, &mO2, col, row, lane);
+          ++blk;
+        }
+      }
+    }
+    if (lane == 0) tma_wait_group0();                          // shared memory must outlive the last TMA store's read
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements per row, `rows` rows `row_pitch` elements apart; box {64, box_rows}, SWIZZLE_128B
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t inner, int64_t rows, int64_t row_pitch, int box_rows);
+
+}  // namespace vbx
+
+using namespace vbx;
+
+static int launch_gemm(int mode, const uint16_t* a, const uint16_t* w, const uint16_t* bias, uint16_t* o0, int64_t o0_pitch, uint16_t* o1,
+                       uint16_t* o2, int64_t M, int64_t n_cols, int64_t K, int64_t w_rows, void* stream) {
+  using namespace gemm;
+  CUtensorMap mA, mW, mO0, mO1, mO2;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&mA, a, K, M, K, kBM)) != VBX_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&mW, w, K, w_rows, K, 128)) != VBX_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&mO0, o0, n_cols, M, o0_pitch, 32)) != VBX_OK) return rc;
+  mO1 = mO0;
+  mO2 = mO0;
+  if (mode == GEGLU && (rc = make_tmap_bf16_2d(&mO1, o1, n_cols, M, o0_pitch, 32)) != VBX_OK) return rc;
+  if (mode != PLAIN && (rc = make_tmap_bf16_2d(&mO2, o2, n_cols, M, n_cols, 32)) != VBX_OK) return rc;
+  const int m_tiles = (int)((M + kBM - 1) / kBM);
+  const int n_tiles = (int)(mode == PLAIN ? (n_cols + 255) / 256 : (n_cols + 127) / 128);
+  const int grid = m_tiles * n_tiles < kNumSM ? m_tiles * n_tiles : kNumSM;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t ce;
+#define VBX_GEMM_LAUNCH(MODE_, SECOND)                                                                                       \
+  ce = cudaFuncSetAttribute(gemm_bf16_kernel<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);          \
+  if (ce != cudaSuccess) return (int)ce;                                                                                     \
+  gemm_bf16_kernel<MODE_><<<grid, kThreads, kSmemBytes, s>>>(mA, mW, mO0, mO1, mO2, bias, (int)M, (int)n_cols, (int)K, m_tiles,  \
+                                                              n_tiles, (int)(SECOND));
+  if (mode == PLAIN) {
+    VBX_GEMM_LAUNCH(PLAIN, 128)
+  } else if (mode == GEGLU) {
+    VBX_GEMM_LAUNCH(GEGLU, n_cols)
+  } else {
+    VBX_GEMM_LAUNCH(GEGLU_NOH, n_cols)
+  }
+#undef VBX_GEMM_LAUNCH
+  return VBX_LAUNCH_RC();
+}
+
+extern "C" int vbx_gemm_bf16(const uint16_t* a, const uint16_t* w, const uint16_t* bias, uint16_t* c, int64_t M, int64_t N, int64_t K,
+                             void* stream) {
+  VBX_REQUIRE(a && w && c, VBX_E_NULL);
+  VBX_REQUIRE(M > 0 && N >= 32 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31) && N % 8 == 0 && K % 8 == 0, VBX_E_SHAPE);
+  VBX_REQUIRE(VBX_ALIGNED16(a) && VBX_ALIGNED16(w) && VBX_ALIGNED16(c) && (!bias || VBX_ALIGNED16(bias)), VBX_E_ALIGN);
+  return launch_gemm(gemm::PLAIN, a, w, bias, c, N, nullptr, nullptr, M, N, K, N, stream);
+}
+
+extern "C" int vbx_ff1_geglu(const uint16_t* x, const uint16_t* w1, const uint16_t* b1, uint16_t* h, uint16_t* g, int64_t M, int64_t Fp,
+                             int64_t K, void* stream) {
+  VBX_REQUIRE(x && w1 && b1 && g, VBX_E_NULL);
+  VBX_REQUIRE(M > 0 && Fp >= 32 && K > 0 && M < (1ll << 31) && Fp < (1ll << 30) && K < (1ll << 31) && Fp % 32 == 0 && K % 8 == 0,
+              VBX_E_SHAPE);
+  VBX_REQUIRE(VBX_ALIGNED16(x) && VBX_ALIGNED16(w1) && VBX_ALIGNED16(b1) && VBX_ALIGNED16(g) && (!h || VBX_ALIGNED16(h)), VBX_E_ALIGN);
+  if (h != nullptr) return launch_gemm(gemm::GEGLU, x, w1, b1, h, 2 * Fp, h + Fp, g, M, Fp, K, 2 * Fp, stream);
+  return launch_gemm(gemm::GEGLU_NOH, x, w1, b1, g, Fp, nullptr, g, M, Fp, K, 2 * Fp, stream);
+}

@@ -1,0 +1,71 @@
+// Operand packing: every fp32 master weight / bias of the trunk -> its bf16 tensor-core operand copy, ALL in one launch.
+//
+// The reference reaches the same state through autocast: each `F.linear` under `torch.autocast(bfloat16)` casts its fp32
+// weight and bias to bf16 at use (trainer.py:267), i.e. ~14 cast kernels per layer per forward (plus zero-padding copies for
+// the GEGLU operands, whose inner width int(8D/3) is not 16-byte aligned).  Here a table of segments
+//   { src f32 [rows x cols], row pitch src_pitch }  ->  { dst bf16, row pitch dst_pitch }
+// is walked by one grid: one warp per row, 16-byte loads where the row allows it.  Destination padding is never written
+// (the caller allocates the operand buffers zero-filled once).
+#include "common.cuh"
+
+namespace vbx {
+
+struct PackSeg {          // mirrors the int64 [n_seg, 6] table built by pack.py
+  const float* src;
+  uint16_t* dst;
+  int64_t rows, cols, src_pitch, dst_pitch;
+};
+
+// row_start: exclusive prefix sum of rows over the segments (int64 [n_seg + 1])
+__global__ void __launch_bounds__(256) pack_bf16_kernel(const PackSeg* __restrict__ segs, const int64_t* __restrict__ row_start,
+                                                         int n_seg) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t total = row_start[n_seg];
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < total; row += warps) {
+    int lo = 0, hi = n_seg;                       // largest s with row_start[s] <= row (warp-uniform search)
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (row_start[mid] <= row) lo = mid; else hi = mid;
+    }
+    const PackSeg sg = segs[lo];
+    const int64_t r = row - row_start[lo];
+    const float* s = sg.src + r * sg.src_pitch;
+    uint16_t* d = sg.dst + r * sg.dst_pitch;
+    const int64_t n = sg.cols;
+    if (((reinterpret_cast<uintptr_t>(s) & 15) == 0) && ((reinterpret_cast<uintptr_t>(d) & 7) == 0)) {
+      const int64_t n4 = n >> 2;
+#pragma unroll 4
+      for (int64_t i = lane; i < n4; i += 32) {
+        const uint4 u = ldg_nc_16(s + 4 * i);
+        __nv_bfloat162 a = f2bf(__uint_as_float(u.x), __uint_as_float(u.y)), b = f2bf(__uint_as_float(u.z), __uint_as_float(u.w));
+        *reinterpret_cast<uint2*>(d + 4 * i) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+      }
+      for (int64_t i = (n4 << 2) + lane; i < n; i += 32) d[i] = __bfloat16_as_ushort(__float2bfloat16_rn(s[i]));
+    } else if (((reinterpret_cast<uintptr_t>(s) & 7) == 0) && ((reinterpret_cast<uintptr_t>(d) & 3) == 0)) {
+      const int64_t n2 = n >> 1;                  // rows of an odd-pitch matrix (e.g. [D, 2730] fp32): 8-byte aligned only
+      for (int64_t i = lane; i < n2; i += 32) {
+        const float2 u = *reinterpret_cast<const float2*>(s + 2 * i);
+        __nv_bfloat162 a = f2bf(u.x, u.y);
+        *reinterpret_cast<uint32_t*>(d + 2 * i) = *reinterpret_cast<uint32_t*>(&a);
+      }
+      if ((n & 1) && lane == 0) d[n - 1] = __bfloat16_as_ushort(__float2bfloat16_rn(s[n - 1]));
+    } else {
+      for (int64_t i = lane; i < n; i += 32) d[i] = __bfloat16_as_ushort(__float2bfloat16_rn(s[i]));
+    }
+  }
+}
+
+}  // namespace vbx
+
+using namespace vbx;
+
+extern "C" int vbx_pack_bf16(const void* segs, const int64_t* row_start, int64_t n_seg, int64_t total_rows, void* stream) {
+  VBX_REQUIRE(segs && row_start, VBX_E_NULL);
+  VBX_REQUIRE(n_seg > 0 && n_seg < (1 << 30) && total_rows > 0, VBX_E_SHAPE);
+  VBX_REQUIRE((reinterpret_cast<uintptr_t>(segs) & 7) == 0, VBX_E_ALIGN);
+  static_assert(sizeof(PackSeg) == 48, "table layout: 6 x int64 per segment");
+  pack_bf16_kernel<<<grid_for(total_rows, 8, 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const PackSeg*>(segs), row_start,
+                                                                                (int)n_seg);
+  return VBX_LAUNCH_RC();
+}

@@ -61,6 +61,10 @@ class FlatGradBucket:
         self._avg = backend == 'nccl'
         for p in self.params:
             p.register_post_accumulate_grad_hook(self._hook)
+            # the packed linear layers (pack.py / ops._LinearW) accumulate fp32 weight gradients straight into these views and
+            # then call the hook themselves (autograd's AccumulateGrad never sees those gradients)
+            p._vbx_inplace_grad = True
+            p._vbx_post_accum = self._hook
 
     # ---- hooks ---------------------------------------------------------------------------------------------------
     def _hook(self, p):

@@ -18,11 +18,44 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
+from . import pack as _pack
 from .ode import odeint_fixed, METHODS
 
 BF16 = torch.bfloat16
 # EXPERIMENT (off by default until timed on a B200): batch the adaptive norms' gamma/beta projections, see ops.batched_affine
 BATCHED_GAMMA_BETA = os.environ.get('VBX_BATCHED_GB', '0') == '1'
+# operand packs (pack.py): bf16 operand copies of all Linear weights refreshed by one launch per optimizer step, fp32 weight
+# gradients accumulated straight into the master gradients, all gamma/beta projections as one batched GEMM.  VBX_PACKED=0
+# falls back to per-use differentiable casts (the reference's autocast behaviour, launch for launch).
+PACKED = os.environ.get('VBX_PACKED', '1') != '0'
+
+
+def _build_pack(root):
+    def builder(pk):
+        for lin in (getattr(root, 'to_embed', None), getattr(root, 'to_pred', None)):
+            lin = lin[0] if isinstance(lin, nn.Sequential) else lin
+            if isinstance(lin, nn.Linear):
+                pk.add(lin.weight)
+                if lin.bias is not None:
+                    pk.add(lin.bias)
+        tmlp = getattr(root, 'sinu_pos_emb', None)
+        if tmlp is not None:
+            pk.add(tmlp[1].weight)
+            pk.add(tmlp[1].bias)
+        tr = root if type(root).__name__ == 'Transformer' else root.transformer
+        _pack.build_for_transformer(pk, tr)
+    return builder
+
+
+def _pack_scope(root):
+    """Context manager making `root`'s OperandPack (refreshed if any parameter changed) the active one for the forward inside."""
+    if not PACKED or _pack.active() is not None:
+        return _pack.use(_pack.active())
+    with torch.inference_mode(False), torch.no_grad():   # operand buffers must never be inference tensors
+        pk = _pack.for_module(root, _build_pack(root))
+        if pk is not None:
+            pk.refresh()
+    return _pack.use(pk)
 
 
 def exists(v):
@@ -253,6 +286,12 @@ def _ff_branch(ff, h):
     operand copies are therefore zero-padded to Fp = roundup(F, 64) -- exact, since gelu(0) * 0 = 0 and the padded
     columns of the second weight are zero."""
     lin1, lin2 = ff[0], ff[3]
+    pk = _pack.active()
+    if pk is not None:
+        ew, eb = pk.lookup(lin1.weight), pk.lookup(lin1.bias)
+        if ew is not None and eb is not None:
+            g = ops.linear_geglu_packed(h, lin1.weight, lin1.bias, ew, eb)
+            return ops.linear(g, lin2.weight, lin2.bias)
     f = lin2.in_features
     fp = _round_up(f, 64)
     if fp == f:
@@ -345,7 +384,15 @@ def transformer_trunk(self, x, mask, cond, n_out):
         mask = mask.contiguous()
 
     batched = {}
-    if BATCHED_GAMMA_BETA and exists(cond_bf16):
+    stack = self.__dict__.get('_vbx_gb_stack') if _pack.active() is not None else None
+    if stack is not None and exists(cond_bf16):
+        # every adaptive norm's (gamma, beta) from ONE batched GEMM on the packed, stacked operands (pack.py)
+        W, bvec, _ = stack
+        norms = [n for layer in self.layers for n in (layer[2], layer[4]) if hasattr(n, 'to_gamma')]
+        params = [t for n in norms for lin in (n.to_gamma, n.to_beta) for t in (lin.weight, lin.bias)]
+        gbs = ops.batched_affine_packed(cond_bf16, W, bvec, params)
+        batched = {id(n): (gbs[2 * i], gbs[2 * i + 1]) for i, n in enumerate(norms)}
+    elif BATCHED_GAMMA_BETA and exists(cond_bf16):
         # every adaptive norm's (gamma, beta) from ONE batched GEMM over the time embedding instead of 2 tiny GEMMs per norm
         norms = [n for layer in self.layers for n in (layer[2], layer[4]) if hasattr(n, 'to_gamma')]
         if norms:
@@ -395,7 +442,8 @@ def transformer_forward(self, x, mask=None, adaptive_rmsnorm_cond=None):
         x32 = torch.cat((self.register_tokens.float()[None].expand(B, -1, -1), x32), dim=1)
         if exists(mask):
             mask = F.pad(mask, (int(self.num_register_tokens), 0), value=True)
-    return transformer_trunk(self, x32.contiguous(), mask, adaptive_rmsnorm_cond, n).to(x.dtype)
+    with _pack_scope(self):
+        return transformer_trunk(self, x32.contiguous(), mask, adaptive_rmsnorm_cond, n).to(x.dtype)
 
 
 Transformer.forward = transformer_forward
@@ -468,6 +516,11 @@ def _time_embedding(self, times):
 
 def _voicebox_body(self, emb, times, self_attn_mask):
     """emb: bf16 [B,N,2*dim_in(+dim_cond_emb)] = cat(x, [cond_emb], cond)  ->  prediction bf16 [B,N,dim_out]."""
+    with _pack_scope(self):
+        return _voicebox_body_inner(self, emb, times, self_attn_mask)
+
+
+def _voicebox_body_inner(self, emb, times, self_attn_mask):
     B, n, _ = emb.shape
     tr = self.transformer
     times = _fix_times(times, B)                                                                  # vp.py:1012-1016
@@ -682,12 +735,13 @@ def duration_predictor_forward(self, *, cond, texts=None, phoneme_ids=None, cond
     cond = curtail_or_pad(cond, phoneme_ids.shape[-1])
     emb = torch.cat((phoneme_emb, cond), dim=-1).to(BF16)
     n = emb.shape[1]
-    h = ops.linear(emb, self.to_embed.weight, self.to_embed.bias)
-    conv = self.conv_embed.dw_conv1d[0]
-    x = ops.convpos_residual_pack(h, conv.weight, conv.bias, self_attn_mask, None)
-    hfin = transformer_trunk(self.transformer, x, self_attn_mask, None, n)
-    lin = self.to_pred[0]
-    return ops.linear(hfin, lin.weight, lin.bias)[..., 0].to(cond.dtype)
+    with _pack_scope(self):
+        h = ops.linear(emb, self.to_embed.weight, self.to_embed.bias)
+        conv = self.conv_embed.dw_conv1d[0]
+        x = ops.convpos_residual_pack(h, conv.weight, conv.bias, self_attn_mask, None)
+        hfin = transformer_trunk(self.transformer, x, self_attn_mask, None, n)
+        lin = self.to_pred[0]
+        return ops.linear(hfin, lin.weight, lin.bias)[..., 0].to(cond.dtype)
 
 
 DurationPredictor.forward = duration_predictor_forward

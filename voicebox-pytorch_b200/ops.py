@@ -9,6 +9,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
+from . import pack as _pack
 from ._lib import call, ptr, stream
 
 BF16 = torch.bfloat16
@@ -114,9 +115,134 @@ def batched_affine(cond_bf16, weights, biases):
     return out.float().unbind(0)
 
 
+def _route_wgrad(w, ew, dy2, x2):
+    """Weight gradient of y = x W_op^T for the fp32 master parameter `w` behind the (possibly padded / row-remapped) operand:
+    accumulated in fp32 straight into w.grad when the flat bucket owns it (returns None), else returned as a new fp32 tensor."""
+    cols = w.numel() // w.shape[0]
+    xs = x2 if x2.shape[1] == cols else x2[:, :cols]
+    sink = _pack.grad_sink(w)
+    full = len(ew.maps) == 1 and ew.maps[0][2] == 0 and ew.maps[0][1] == dy2.shape[1]
+    if sink is not None:
+        s2 = sink.reshape(w.shape[0], cols)
+        for (p0, cnt, o0) in ew.maps:
+            _pack.accumulate_wgrad(s2[p0:p0 + cnt], dy2.t() if full else dy2[:, o0:o0 + cnt].t(), xs)
+        _pack.sink_done(w)
+        return None
+    parts = [_pack.wgrad_fp32(dy2.t() if full else dy2[:, o0:o0 + cnt].t(), xs) for (p0, cnt, o0) in sorted(ew.maps)]
+    return (parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)).reshape(w.shape)
+
+
+def _route_bgrad(b, eb, db32):
+    """db32: fp32 [op width] column sums of dy.  Same routing for the bias parameter."""
+    maps = eb.maps if eb is not None else [(0, b.numel(), 0)]
+    sink = _pack.grad_sink(b)
+    if sink is not None:
+        for (p0, cnt, o0) in maps:
+            sink[p0:p0 + cnt].add_(db32[o0:o0 + cnt])
+        _pack.sink_done(b)
+        return None
+    parts = [db32[o0:o0 + cnt] for (p0, cnt, o0) in sorted(maps)]
+    return parts[0].clone() if len(parts) == 1 else torch.cat(parts)
+
+
+class _LinearW(torch.autograd.Function):
+    """y = x W^T + b on the packed bf16 operands of the fp32 master parameters (w, b): the forward is the library GEMM, the
+    backward routes dW / db to the masters in fp32 (pack.py) instead of through a differentiable cast."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, ew, eb):
+        shp = x.shape
+        x2 = _c(x.reshape(-1, shp[-1]))
+        y = F.linear(x2, ew.op, None if b is None else (eb.op if eb is not None else cast_bf16(b)))
+        ctx.save_for_backward(x2)
+        ctx.misc = (w, b, ew, eb, shp)
+        return y.reshape(shp[:-1] + (y.shape[-1],))
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x2,) = ctx.saved_tensors
+        w, b, ew, eb, shp = ctx.misc
+        dy2 = _c(dy.reshape(-1, dy.shape[-1]))
+        dx = (dy2 @ ew.op).reshape(shp) if ctx.needs_input_grad[0] else None
+        dw = _route_wgrad(w, ew, dy2, x2) if ctx.needs_input_grad[1] else None
+        db = None
+        if b is not None and ctx.needs_input_grad[2]:
+            db = _route_bgrad(b, eb, dy2.sum(dim=0, dtype=torch.float32))
+        return dx, dw, db, None, None
+
+
+class _BatchedAffineW(torch.autograd.Function):
+    """All K adaptive-norm projections y[k] = cond W[k]^T + b[k] (vp.py:259-260, 273) as ONE batched GEMM on the packed, stacked
+    operands W [K, D, C] / bvec [K, D]; returns fp32 [K, B, D].  Backward: dcond as ONE GEMM over the stacked weights, the K
+    weight gradients as fp32-accumulating GEMMs straight into the master gradients, the bias gradients with one reduction."""
+
+    @staticmethod
+    def forward(ctx, cond, W, bvec, *params):
+        K, D, C = W.shape
+        B = cond.shape[0]
+        out = torch.baddbmm(bvec[:, None, :], cond.unsqueeze(0).expand(K, B, C), W.transpose(1, 2))   # [K, B, D] bf16
+        ctx.save_for_backward(cond)
+        ctx.misc = (W, params)
+        return out.float()
+
+    @staticmethod
+    def backward(ctx, dout):
+        (cond,) = ctx.saved_tensors
+        W, params = ctx.misc
+        K, B, D = dout.shape
+        d16 = dout.to(BF16)
+        dcond = None
+        if ctx.needs_input_grad[0]:
+            dcond = d16.permute(1, 0, 2).reshape(B, K * D) @ W.reshape(K * D, -1)
+        db_all = dout.sum(dim=1)                                                         # fp32 [K, D]
+        grads, b_sinks, b_vals = [], [], []
+        for k in range(K):
+            w, b = params[2 * k], params[2 * k + 1]
+            gw = gb = None
+            if ctx.needs_input_grad[3 + 2 * k]:
+                sink = _pack.grad_sink(w)
+                if sink is not None:
+                    _pack.accumulate_wgrad(sink, d16[k].t(), cond)
+                    _pack.sink_done(w)
+                else:
+                    gw = _pack.wgrad_fp32(d16[k].t(), cond)
+            if ctx.needs_input_grad[4 + 2 * k]:
+                sb = _pack.grad_sink(b)
+                if sb is not None:
+                    b_sinks.append(sb)
+                    b_vals.append(db_all[k])
+                else:
+                    gb = db_all[k].clone()
+            grads += [gw, gb]
+        if b_sinks:
+            torch._foreach_add_(b_sinks, b_vals)
+            for k in range(K):
+                if _pack.grad_sink(params[2 * k + 1]) is not None:
+                    _pack.sink_done(params[2 * k + 1])
+        return (dcond, None, None, *grads)
+
+
+def batched_affine_packed(cond_bf16, W, bvec, params):
+    """-> tuple of K contiguous fp32 [B, D] tensors (gamma_0, beta_0, gamma_1, ...) from the packed stack (pack.py)."""
+    if torch.is_grad_enabled() and (cond_bf16.requires_grad or any(p.requires_grad for p in params)):
+        out = _BatchedAffineW.apply(cond_bf16, W, bvec, *params)
+    else:
+        K, D, C = W.shape
+        out = torch.baddbmm(bvec[:, None, :], cond_bf16.unsqueeze(0).expand(K, cond_bf16.shape[0], C), W.transpose(1, 2)).float()
+    return out.unbind(0)
+
+
 def linear(x, weight, bias=None, tag=''):
-    """bf16 library GEMM (cuBLASLt via torch), fp32 accumulate: vp.py:320, 333, 345, 348, 1078, 1092 under autocast."""
-    return F.linear(x, cast_bf16(weight, tag + 'w'), cast_bf16(bias, tag + 'b'))
+    """bf16 library GEMM (cuBLASLt via torch), fp32 accumulate: vp.py:320, 333, 345, 348, 1078, 1092 under autocast.
+    With an active OperandPack (pack.py) the bf16 operands are the pre-packed copies and the gradients go to the fp32 masters."""
+    pk = _pack.active()
+    ew = pk.lookup(weight) if pk is not None else None
+    eb = pk.lookup(bias) if (pk is not None and bias is not None) else None
+    if ew is None or ew.op.dim() != weight.dim() or (bias is not None and (eb is None or eb.op.dim() != 1)):
+        return F.linear(x, cast_bf16(weight, tag + 'w'), cast_bf16(bias, tag + 'b'))   # not packed (or a stacked operand)
+    if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)):
+        return _LinearW.apply(x, weight, bias, ew, eb)
+    return F.linear(x, ew.op, None if bias is None else eb.op)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -221,40 +347,100 @@ def geglu(h):
     return _Geglu.apply(h)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# tcgen05 GEMM with fused epilogues (csrc/gemm.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+import os as _os
+
+# FF1 + bias + GEGLU as ONE tcgen05 kernel instead of cuBLASLt GEMM + geglu_fwd.  'auto' (default): where it was measured faster
+# on the B200; '1' / '0' force it on / off.
+FUSED_FF1 = _os.environ.get('VBX_FUSED_FF1', '0')
+
+
+def gemm_bf16(a, w, bias=None):
+    """C = a w^T (+ bias) on the hand-written tcgen05 GEMM: a bf16 [..., K], w bf16 [N, K], bias bf16 [N] -> bf16 [..., N]."""
+    a2 = _c(a.reshape(-1, a.shape[-1]))
+    M, K = a2.shape
+    N = w.shape[0]
+    c = torch.empty((M, N), device=a.device, dtype=BF16)
+    call('vbx_gemm_bf16', ptr(a2), ptr(_c(w)), ptr(bias), ptr(c), M, N, K, stream())
+    return c.reshape(a.shape[:-1] + (N,))
+
+
+def ff1_geglu(x2, w_op, b_op, need_h):
+    """x2 bf16 [T, K], w_op bf16 [2Fp, K], b_op bf16 [2Fp] -> (h bf16 [T, 2Fp] or None, g bf16 [T, Fp]) in one launch."""
+    T, K = x2.shape
+    fp = w_op.shape[0] // 2
+    h = torch.empty((T, 2 * fp), device=x2.device, dtype=BF16) if need_h else None
+    g = torch.empty((T, fp), device=x2.device, dtype=BF16)
+    call('vbx_ff1_geglu', ptr(x2), ptr(w_op), ptr(b_op), ptr(h), ptr(g), T, fp, K, stream())
+    return h, g
+
+
+def _use_fused_ff1(fp, k):
+    return FUSED_FF1 == '1' and fp % 32 == 0 and k % 8 == 0
+
+
 class _LinearGeglu(torch.autograd.Function):
     """g = GEGLU(x @ w^T + b)  (vp.py:345-346) as ONE autograd node: the backward gets the Linear's bias gradient as a by-product
     of the GEGLU backward kernel (column sums of dh held in registers) instead of a separate reduction pass over dh."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, ew=None, eb=None):
+        """w, b: the bf16 operands themselves (ew is None), or the fp32 master parameters behind the packed operands ew / eb."""
         shp = x.shape
         x2 = _c(x.reshape(-1, shp[-1]))
-        h = F.linear(x2, w, b)                     # bf16 library GEMM [T, 2Fp]
-        T, two_f = h.shape
-        out = torch.empty((T, two_f // 2), device=h.device, dtype=BF16)
-        call('vbx_geglu_fwd', ptr(h), ptr(out), T, two_f // 2, stream())
-        ctx.save_for_backward(x2, w, h)
-        ctx.shp = shp
+        w_op, b_op = (w, b) if ew is None else (ew.op, eb.op)
+        if _use_fused_ff1(w_op.shape[0] // 2, x2.shape[1]):
+            h, out = ff1_geglu(x2, _c(w_op), _c(b_op), True)     # tcgen05 GEMM + bias + GEGLU epilogue, h written once
+            T, two_f = h.shape
+        else:
+            h = F.linear(x2, w_op, b_op)           # bf16 library GEMM [T, 2Fp]
+            T, two_f = h.shape
+            out = torch.empty((T, two_f // 2), device=h.device, dtype=BF16)
+            call('vbx_geglu_fwd', ptr(h), ptr(out), T, two_f // 2, stream())
+        ctx.save_for_backward(x2, h)
+        ctx.misc = (shp, w, b, ew, eb)
         return out.reshape(shp[:-1] + (two_f // 2,))
 
     @staticmethod
     def backward(ctx, dout):
-        x2, w, h = ctx.saved_tensors
+        x2, h = ctx.saved_tensors
+        shp, w, b, ew, eb = ctx.misc
         T, two_f = h.shape
         dout = _c(dout.reshape(T, two_f // 2))
         dh = torch.empty_like(h)
         db = torch.zeros((two_f,), device=h.device, dtype=torch.float32)
         call('vbx_geglu_bwd', ptr(h), ptr(dout), ptr(dh), ptr(db), T, two_f // 2, stream())
-        dx = (dh @ w).reshape(ctx.shp) if ctx.needs_input_grad[0] else None
-        dw = dh.t() @ x2 if ctx.needs_input_grad[1] else None
-        return dx, dw, db.to(BF16) if ctx.needs_input_grad[2] else None
+        w_op = w if ew is None else ew.op
+        dx = (dh @ w_op).reshape(shp) if ctx.needs_input_grad[0] else None
+        if ew is None:
+            dw = dh.t() @ x2 if ctx.needs_input_grad[1] else None
+            return dx, dw, (db.to(BF16) if ctx.needs_input_grad[2] else None), None, None
+        dw = _route_wgrad(w, ew, dh, x2) if ctx.needs_input_grad[1] else None
+        dbg = _route_bgrad(b, eb, db) if ctx.needs_input_grad[2] else None
+        return dx, dw, dbg, None, None
 
 
 def linear_geglu(x, w_bf16, b_bf16):
     """x bf16 [..., D], w bf16 [2Fp, D], b bf16 [2Fp] -> bf16 [..., Fp]."""
     if torch.is_grad_enabled() and (x.requires_grad or w_bf16.requires_grad or b_bf16.requires_grad):
         return _LinearGeglu.apply(x, w_bf16, b_bf16)
-    return geglu(F.linear(x, w_bf16, b_bf16))
+    return _ff1_nograd(x, w_bf16, b_bf16)
+
+
+def _ff1_nograd(x, w_op, b_op):
+    if _use_fused_ff1(w_op.shape[0] // 2, x.shape[-1]):
+        _, g = ff1_geglu(_c(x.reshape(-1, x.shape[-1])), _c(w_op), _c(b_op), False)   # inference: h is never written
+        return g.reshape(x.shape[:-1] + (g.shape[-1],))
+    return geglu(F.linear(x, w_op, b_op))
+
+
+def linear_geglu_packed(x, w, b, ew, eb):
+    """Same on the packed operands ew / eb of the fp32 master parameters w [2F, D], b [2F] (pack.py)."""
+    if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or b.requires_grad):
+        return _LinearGeglu.apply(x, w, b, ew, eb)
+    return _ff1_nograd(x, ew.op, eb.op)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
