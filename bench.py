@@ -71,13 +71,49 @@ CPU_BATCH = 2          # cfg3 at reduced batch B=2, per-s
 
 
 def _host_cores():
+    """CPUs this process may actually use: the affinity mask, capped by the cgroup CPU quota when there is one."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()
+        if quota != 'max':
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
 
 
-def _cpu_step_fn(depth, flash, batch):
+_THREADS = {}
+
+
+def _calibrate_threads(cores):
+    """torch's intra-op thread count for the CPU arm.  'All host threads' is the intent, but on a shared 128-thread host one
+    oversubscribed OpenMP team can be 10x slower than a quarter of it (trip 1: 24.6 s vs ~2 s for the same step): time one
+    forward of the depth-2 sample at {cores/8, cores/4, cores/2, cores} (>= 8), ascending, and keep the fastest."""
+    if cores in _THREADS:
+        return _THREADS[cores]
+    cands = sorted({max(8, min(cores, c)) for c in (cores, cores // 2, cores // 4, cores // 8)})
+    if len(cands) == 1:
+        _THREADS[cores] = (cands[0], {})
+        return _THREADS[cores]
+    fn, _ = _cpu_step_fn(CPU_DEPTHS[0], True, CPU_BATCH, backward=False)   # forward only: a third of the cost, same scaling
+    timing = {}
+    for t in cands:                                  # ascending; stop as soon as more threads stopped helping
+        torch.set_num_threads(t)
+        fn()
+        t0 = time.perf_counter()
+        fn()
+        timing[t] = time.perf_counter() - t0
+        if timing[t] > 1.25 * min(timing.values()):
+            break
+    best = min(timing, key=timing.get)
+    _THREADS[cores] = (best, {str(k): round(v, 2) for k, v in timing.items()})
+    return _THREADS[cores]
+
+
+def _cpu_step_fn(depth, flash, batch, backward=True):
     """-> (callable running ONE fp32 forward+backward of the CFM loss on the CPU, kind).  kind 'reference': the UNMODIFIED
     reference package (baseline/_ref or /root/reference, stub-imported by oracle/ref_import.py) through its own public API
     `ConditionalFlowMatcherWrapper(x)`; kind 'port': oracle/voicebox_oracle.py (math-path attention only) when no copy of the
@@ -98,6 +134,9 @@ def _cpu_step_fn(depth, flash, batch):
         w = vp.ConditionalFlowMatcherWrapper(voicebox=vb)
 
         def step():
+            if not backward:
+                with torch.no_grad():
+                    return w(x1)
             w.zero_grad(set_to_none=True)
             w(x1).backward()
         return step, 'reference'
@@ -111,6 +150,9 @@ def _cpu_step_fn(depth, flash, batch):
         cfg = dict(depth=depth, heads=HEADS, num_register_tokens=REG, qk_norm=True, condition_on_text=False)
 
         def step():
+            if not backward:
+                with torch.no_grad():
+                    return O.cfm_loss(sdg, cfg, x1)
             for v in sdg.values():
                 if v.grad is not None:
                     v.grad = None
@@ -136,7 +178,8 @@ def cpu_reference_frames_per_sec(flash=False, steps=3, warmup=2):
     to_pred, loss) is t2 - 2 * per_layer, so the full model is fixed + 24 * per_layer -- no cold iteration is ever counted.
     frames/s = CPU_BATCH * SEQ / full_step_seconds."""
     cores = _host_cores()
-    torch.set_num_threads(cores)
+    threads, calib = _calibrate_threads(cores)
+    torch.set_num_threads(threads)
     warmup, steps = max(2, warmup), max(3, steps)
     med, raw, kind = {}, {}, None
     for d in CPU_DEPTHS:
@@ -148,7 +191,8 @@ def cpu_reference_frames_per_sec(flash=False, steps=3, warmup=2):
     fixed = max(med[d0] - d0 * per_layer, 0.0)
     full = fixed + DEPTH * per_layer
     sampled = sum(sum(v) for v in raw.values())
-    return dict(value=CPU_BATCH * SEQ / full, unit='frames/s', cores=cores, kind=kind, attn_flash=bool(flash),
+    return dict(value=CPU_BATCH * SEQ / full, unit='frames/s', cores=threads, host_cpus=cores, thread_calibration_s=calib, kind=kind,
+                attn_flash=bool(flash),
                 est_full_step_s=full, per_layer_s=per_layer, fixed_s=fixed, timed_s={str(k): v for k, v in med.items()},
                 sample=f'{"reference package" if kind == "reference" else "oracle port"} fp32 fwd+bwd of the CFM loss, dim{DIM} seq{SEQ} heads{HEADS} '
                        f'batch {CPU_BATCH}, attn_flash={bool(flash)}: depth {d0} -> {med[d0]:.2f} s, depth {d1} -> {med[d1]:.2f} s (median of {steps} '

@@ -238,7 +238,10 @@ def test_trainable_proj_in_receives_gradients(vbx):
     """vp.py:911-914, 1000, 1007: with audio_enc_dec.latent_dim != dim the reference trains `proj_in`.  The one-pass
     embed_concat kernel has no grad_fn, so it must not be taken when x / cond carry a graph."""
     torch.manual_seed(0)
-    vb = vbx.VoiceBox(dim=128, depth=2, heads=2, time_hidden_dim=128, audio_enc_dec=_ToyCodec(), condition_on_text=False)
+    # attn_qk_norm=False: with the scale-10 qk-norm softmax the loss is a near-discontinuous function of the inputs (winner flips)
+    # and a finite difference over eps = 0.05 does not see the (huge, rapidly varying) analytic derivative
+    vb = vbx.VoiceBox(dim=128, depth=2, heads=2, time_hidden_dim=128, audio_enc_dec=_ToyCodec(), condition_on_text=False,
+                      attn_qk_norm=False)
     w = vbx.ConditionalFlowMatcherWrapper(voicebox=vb).cuda()
     assert isinstance(vb.proj_in, torch.nn.Linear)
     x1 = torch.randn(2, 96, 32, device='cuda')
