@@ -28,11 +28,13 @@ for it in range(3):
     o.backward(do)
     torch.cuda.synchronize()
 t = trace.cpu().view(8, 16, 8)
-names = {0: ('bwd MMA', ['pre', 'QD_FULL', 'ST_FREE', 'S issued', 'preDS', 'DS_FULL', 'G issued']),
+names = {0: ('bwd MMA A (S^T, dP^T)', ['pre', 'QD_FULL', 'ST_FREE', 'S issued', 'preDS', 'DS_FULL', 'G issued']),
+         5: ('bwd MMA B (dV, dK)', ['QD_FULL', 'DS_FULL', 'issued']),
+         6: ('bwd MMA C (dQ)', ['pre', 'DS_FULL', 'DQ_FREE', 'issued']),
          1: ('bwd compute t0', ['top', 'bar1', 'ST_FULL', 'math done', 'flushed', 'stored', 'arrived']),
          2: ('bwd producer', ['QD_EMPTY ok']),
          3: ('fwd MMA', ['pre', 'K_FULL', 'S_FREE', 'S issued', 'V_FULL', 'P_FULL', 'PV issued']),
-         4: ('fwd softmax t0', ['top', 'S_FULL', 'pass1', 'bar', 'pass2', 'P arrived', 'O(j-1) accumulated (between bar and pass2)'])}
+         4: ('fwd softmax t0 (v2)', ['top', 'S_FULL', 'max exchanged', '-', 'exp+P stored', 'P arrived'])}
 for role, (nm, pts) in names.items():
     base = int(t[role][t[role] > 0].min()) if (t[role] > 0).any() else 0
     print(f'== {nm}  (clk relative to first stamp of this role; columns: {pts})')

@@ -8,6 +8,7 @@
 // Replaces attend.py:100-137 (math path: einsum, scale, masked_fill(-finfo.max), softmax, einsum) and the SDPA
 // delegation attend.py:71-98; the head merge 'b h n d -> b n (h d)' (vp.py:332) is folded into the epilogue store.
 #include <cfloat>
+#include <cstdlib>
 #include <mutex>
 
 #include "umma.cuh"
@@ -26,7 +27,7 @@ constexpr uint32_t kTileBytes = kBN * kDh * 2;  // 16 KB
 // is 7/8 padding.  With the flag on, its S / S^T / dP^T GEMMs run with N = roundup(valid, 16) instead of 128, its P V / dV /
 // dK GEMMs with valid/16 K-steps instead of 8, and the softmax / exp code skips (warp-uniformly) chunks that are all padding.
 #ifndef VBX_EXP_TAIL
-#define VBX_EXP_TAIL 0
+#define VBX_EXP_TAIL 1   // on since round 2: parity-green on every tail geometry, -5 % backward time (profiles/README.md)
 #endif
 // EXPERIMENT (backward), off in libvbx_sm100a.so: VBX_EXP_DSBUF=1 double-buffers dS^T in shared memory (paid for by
 // staging dQ one 32-column half at a time) and releases P^T (TMEM) with its own barrier right after the dV GEMM.  In the
@@ -34,7 +35,22 @@ constexpr uint32_t kTileBytes = kBN * kDh * 2;  // 16 KB
 // so per tile the GEMM group (~1900 clk in the trace) and the store phase (~800 clk) run back to back; with the flag the
 // stores of tile i+1 overlap the dK/dQ GEMMs of tile i.
 #ifndef VBX_EXP_DSBUF
-#define VBX_EXP_DSBUF 0
+#define VBX_EXP_DSBUF 1  // on since round 2: parity-green, -4 % backward time; required by VBX_BWD_ISSUERS == 3
+#endif
+
+// Backward: number of tcgen05.mma ISSUING warps.  One thread sustains one tcgen05.mma per ~55-70 clk whatever its shape (ptxas
+// wraps every MMA in an ELECT / BRA.U.ANY loop; tools/umma_bench.py: N = 64 TS-mode MMAs retire at 66 clk each from one
+// issuing warp, 33 clk from two, 32 clk from three = the nominal rate).  The backward issues 40 MMAs per tile pair: from one
+// warp that is ~2500 clk of pure issue against ~1540 clk of tensor-pipe time, and the trace showed the MMA warp issuing
+// back to back for the whole tile.  With 3: warp A = S^T / dP^T of the next tile, warp B = dV + dK, warp C = dQ.
+#ifndef VBX_BWD_ISSUERS
+#define VBX_BWD_ISSUERS 3
+#endif
+#if VBX_BWD_ISSUERS != 1 && VBX_BWD_ISSUERS != 3
+#error "VBX_BWD_ISSUERS must be 1 or 3"
+#endif
+#if VBX_BWD_ISSUERS == 3 && !VBX_EXP_DSBUF
+#error "three issuing warps need the double-buffered dS^T tile (VBX_EXP_DSBUF=1)"
 #endif
 
 // ---- optional pipeline trace (built only with -DVBX_TRACE into lib/libvbx_trace.so; tools/trace_attn.py reads it) ----------
@@ -376,6 +392,300 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
 }
 
 // =====================================================================================================================
+// forward, second generation (default; VBX_ATTN_FWD_V1=1 selects the kernel above for A/B runs)
+// =====================================================================================================================
+// Same CTA shape, roles, barriers and TMEM map as the first kernel (S: [0,128)  O: [128,192)  P: [192,256), 2 CTAs / SM).  What
+// changed is the per-tile dependency chain of the softmax warps, which -- not any pipe -- bounded the first kernel (two CTAs x
+// ~3700 clk per tile against a 1024-clk MUFU floor; profiles/README.md):
+//   * ONE pass over S: each thread pulls its 64 logits out of TMEM once, releases S to the MMA warp at once (S_{j+1} = Q K^T
+//     runs under this tile's exponentials), and keeps them in registers for the max and the exp.
+//   * O stays in TMEM: P_j V_j accumulates straight into the O columns (no per-tile read-modify-write of O in registers).
+//   * LAZY rescale: the running max used for the exponentials is only advanced (and O, l rescaled through one TMEM
+//     load / multiply / store) when the true row max has grown by more than 2^8 -- p <= 256 is harmless in bf16 / fp32 and the
+//     final normalisation by l (accumulated against the same stale max) cancels it exactly.  After the first tiles of a row
+//     the rescale is rare, so the P_{j-1} V_{j-1} -> O_j dependency leaves the critical path.
+//   * the two threads of a row agree on the row max through a 64-thread named barrier of just their two warps.
+//   * the tail key tile (N' = 8*128 + 16) runs its S GEMM at N = roundup16(valid), its P V GEMM over valid/16 K-steps, and
+//     32-column chunks that are all padding are skipped outright (no TMEM traffic, no exponentials).
+// 64-thread named barrier of the two warps that own the same 32 query rows (ids 2..5; literal ids so that ptxas does not
+// reserve all 16 hardware barriers for the CTA)
+VBX_DEVINL void pair_sync(int quarter) {
+  switch (quarter) {
+    case 0: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 5, 64;" ::: "memory"); break;
+  }
+}
+
+__global__ void __launch_bounds__(fwd::kThreads, 2)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
+                 const __grid_constant__ CUtensorMap mv, const uint8_t* __restrict__ key_mask, float scale_log2,
+                 uint16_t* __restrict__ o, float* __restrict__ lse, int N, int H) {
+  using namespace fwd;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + NUM_BARS * 8);
+  float* s_bias = reinterpret_cast<float*>(smem + kOffBias);  // [2][128]: 0 / -FLT_MAX / -inf per key of the tile
+  float* s_max = reinterpret_cast<float*>(smem + kOffMax);    // [2][2][128]: per-tile partial row max of each column half
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kBM, h = blockIdx.y, b = blockIdx.z;
+  const int nkv = (N + kBN - 1) / kBN;
+  const int n_tail = (N - (nkv - 1) * kBN + 15) & ~15;        // GEMM width of the last key tile (16 .. 128)
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    mbar_init(&bars[Q_FULL], 1);
+    mbar_init(&bars[K_FULL], 1);
+    mbar_init(&bars[K_FULL + 1], 1);
+    mbar_init(&bars[K_EMPTY], 1);
+    mbar_init(&bars[K_EMPTY + 1], 1);
+    mbar_init(&bars[V_FULL], 1);
+    mbar_init(&bars[V_FULL + 1], 1);
+    mbar_init(&bars[V_EMPTY], 1);
+    mbar_init(&bars[V_EMPTY + 1], 1);
+    mbar_init(&bars[S_FULL], 1);
+    mbar_init(&bars[S_FREE], 256);
+    mbar_init(&bars[P_FULL], 256);
+    mbar_init(&bars[O_FULL], 1);
+    fence_barrier_init();
+  }
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&mq);
+    tma_prefetch_desc(&mk);
+    tma_prefetch_desc(&mv);
+  }
+  if (warp == 9) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ------------------------------------------------ TMA producer ------------------------------------------------
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars[Q_FULL], kTileBytes);
+      tma_load_4d(smem + kOffQ, &mq, &bars[Q_FULL], 0, q0, h, b);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        if (j + 2 < nkv) {  // warm L2 two tiles ahead
+          tma_prefetch_l2_4d(&mk, 0, (j + 2) * kBN, h, b);
+          tma_prefetch_l2_4d(&mv, 0, (j + 2) * kBN, h, b);
+        }
+        mbar_wait(&bars[K_EMPTY + st], ((j >> 1) & 1) ^ 1);  // S(j-2) has retired
+        mbar_arrive_expect_tx(&bars[K_FULL + st], kTileBytes);
+        tma_load_4d(smem + kOffK + st * kTileBytes, &mk, &bars[K_FULL + st], 0, j * kBN, h, b);
+        mbar_wait(&bars[V_EMPTY + st], ((j >> 1) & 1) ^ 1);  // PV(j-2) has retired
+        mbar_arrive_expect_tx(&bars[V_FULL + st], kTileBytes);
+        tma_load_4d(smem + kOffV + st * kTileBytes, &mv, &bars[V_FULL + st], 0, j * kBN, h, b);
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------ MMA issuer --------------------------------------------------
+    constexpr uint32_t idesc_s = make_idesc(kBM, kBN, false, false);  // S = Q K^T      (both K-major)
+    constexpr uint32_t idesc_o = make_idesc(kBM, kDh, false, true);   // O += P V       (V is MN-major: [keys][d])
+    const uint64_t dQ = sdesc_k0(smem_u32(smem + kOffQ));
+    const uint64_t dK0 = sdesc_k0(smem_u32(smem + kOffK)), dV0 = sdesc_mn0(smem_u32(smem + kOffV));
+    const bool leader = lane == 0;
+    const uint32_t idesc_s_tail = make_idesc(kBM, n_tail, false, false);
+    mbar_wait(&bars[Q_FULL], 0);
+    auto issue_s = [&](int j) {  // S_j = Q K_j^T
+      const int st = j & 1;
+      const uint64_t dK = dK0 + (uint64_t)st * (kTileBytes >> 4);
+      const uint32_t idesc_sj = (j == nkv - 1) ? idesc_s_tail : idesc_s;
+      TRACE(3, j, 0);
+      mbar_wait(&bars[K_FULL + st], (j >> 1) & 1);
+      TRACE(3, j, 1);
+      mbar_wait(&bars[S_FREE], (j & 1) ^ 1);  // the softmax warps hold S_{j-1} in registers
+      TRACE(3, j, 2);
+      tc_fence_after();
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < kDh / 16; ++k) umma_bf16(tmem_base, dQ + koff_k(k), dK + koff_k(k), idesc_sj, k > 0);
+        umma_commit(&bars[S_FULL]);
+        umma_commit(&bars[K_EMPTY + st]);
+      }
+      __syncwarp();
+      TRACE(3, j, 3);
+    };
+    issue_s(0);
+    for (int j = 0; j < nkv; ++j) {
+      const int st = j & 1;
+      const uint64_t dV = dV0 + (uint64_t)st * (kTileBytes >> 4);
+      if (j + 1 < nkv) issue_s(j + 1);  // only needs S released, which now happens right after the softmax warps' single load
+      mbar_wait(&bars[V_FULL + st], (j >> 1) & 1);
+      TRACE(3, j, 4);
+      mbar_wait(&bars[P_FULL], j & 1);
+      TRACE(3, j, 5);
+      tc_fence_after();
+      if (leader) {
+        const int ksteps = (j == nkv - 1) ? n_tail / 16 : kBN / 16;
+#pragma unroll
+        for (int k = 0; k < kBN / 16; ++k)  // A = P from TMEM: 8 columns (16 keys) per K-step; O accumulates across tiles
+          if (k < ksteps) umma_bf16_ts(tmem_base + kColO, tmem_base + kColP + k * 8, dV + koff_mn(k), idesc_o, (j > 0) || (k > 0));
+        umma_commit(&bars[O_FULL]);
+        umma_commit(&bars[V_EMPTY + st]);
+      }
+      __syncwarp();
+      TRACE(3, j, 6);
+    }
+  } else {
+    // ------------------------------------------------ softmax: two threads per query row ---------------------------
+    const int half = warp >> 2;                 // which 64 key columns of S / which 32 columns of O
+    const int r = (warp & 3) * 32 + lane;       // query row of the tile == TMEM lane
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    float m_used = -FLT_MAX, l = 0.f;           // max the exponentials are taken against; partial row sum of this half
+
+    for (int j = 0; j < nkv; ++j) {
+      const int k0 = j * kBN;
+      const bool masked_tile = (key_mask != nullptr) || (k0 + kBN > N);  // CTA-uniform
+      const float* bias = s_bias + (j & 1) * kBN + half * 64;
+      if (masked_tile) {
+        if (half == 0) {
+          const int key = k0 + r;
+          float v = 0.f;
+          if (key >= N) v = -INFINITY;                                           // the key does not exist
+          else if (key_mask != nullptr && !key_mask[(int64_t)b * N + key]) v = -FLT_MAX;  // masked_fill(-finfo.max)
+          s_bias[(j & 1) * kBN + r] = v;
+        }
+        named_bar_sync(1, 256);
+      }
+      const int valid = N - k0;                                  // >= 128 except in the tail tile
+      const bool live0 = half * 64 < valid, live1 = half * 64 + 32 < valid;   // warp-uniform: chunk holds at least one key
+      if (threadIdx.x == 0) TRACE(4, j, 0);
+      mbar_wait(&bars[S_FULL], j & 1);
+      if (threadIdx.x == 0) TRACE(4, j, 1);
+      tc_fence_after();
+      float s[64];
+      {
+        uint32_t* su = reinterpret_cast<uint32_t*>(s);
+        if (live0) tmem_ld32_issue(t_lane + half * 64, su);
+        if (live1) tmem_ld32_issue(t_lane + half * 64 + 32, su + 32);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(&bars[S_FREE]);                                // this thread's part of S is in registers
+      // local max over this thread's live columns (log2 domain)
+      float mx = -FLT_MAX;
+      if (masked_tile) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (!(c ? live1 : live0)) continue;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float bb = bias[c * 32 + i];
+            float t = fmaf(s[c * 32 + i], scale_log2, bb);
+            // columns >= n_tail of the tail tile were not written by the narrowed GEMM (stale bits, possibly NaN): select
+            t = (bb == -INFINITY) ? -INFINITY : t;
+            s[c * 32 + i] = t;
+            mx = fmaxf(mx, t);
+          }
+        }
+      } else {
+        float m4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+#pragma unroll
+        for (int i = 0; i < 64; ++i) m4[i & 3] = fmaxf(m4[i & 3], s[i]);
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale_log2;  // scale > 0
+      }
+      s_max[((j & 1) * 2 + half) * kBM + r] = mx;
+      pair_sync(warp & 3);
+      mx = fmaxf(mx, s_max[((j & 1) * 2 + (half ^ 1)) * kBM + r]);
+      if (threadIdx.x == 0) TRACE(4, j, 2);
+      bool o_ready = false;                                      // O_FULL(j-1) already waited for in this tile
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const float m_new = fmaxf(m_used, mx);
+        const bool need = (m_new - m_used) > 8.0f;               // lazy: only when p could exceed 2^8
+        if (__any_sync(0xffffffffu, need)) {                     // TMEM accesses are warp-wide: lanes that do not need it use 1
+          const float alpha = need ? ex2(m_used - m_new) : 1.0f;
+          mbar_wait(&bars[O_FULL], (j - 1) & 1);                 // P_{j-1} V_{j-1} has been accumulated
+          tc_fence_after();
+          o_ready = true;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {                          // 16 columns at a time: s[64] is live across this block
+            float ov[16];
+            tmem_ld16(t_lane + kColO + half * 32 + c * 16, ov);
+            uint32_t ou[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ou[i] = __float_as_uint(ov[i] * alpha);
+            tmem_st16(t_lane + kColO + half * 32 + c * 16, ou);
+          }
+          l *= alpha;
+          if (need) m_used = m_new;
+        }
+      }
+      const float neg_m = -m_used;
+      // exponentials, partial row sum, P -> TMEM (bf16 pairs: column kColP + key/2 of this row's lane)
+      float rowsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (!(c ? live1 : live0)) continue;                      // all-padding chunk: its K-steps are not issued either
+        float* sc = s + c * 32;
+        if (masked_tile) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sc[i] = ex2(sc[i] + neg_m);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sc[i] = VBX_EX2_AT(i, fmaf(sc[i], scale_log2, neg_m));  // every key exists: no -inf here
+        }
+        float r4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r4[i & 3] += sc[i];
+        rowsum += (r4[0] + r4[1]) + (r4[2] + r4[3]);
+        uint32_t pk[16];
+#pragma unroll
+        for (int x = 0; x < 16; ++x) {
+          __nv_bfloat162 t2 = f2bf(sc[2 * x], sc[2 * x + 1]);
+          pk[x] = *reinterpret_cast<uint32_t*>(&t2);
+        }
+        if (j > 0 && !o_ready) {                                 // P is single-buffered: P_{j-1} V_{j-1} must have read it
+          mbar_wait(&bars[O_FULL], (j - 1) & 1);
+          tc_fence_after();
+          o_ready = true;
+        }
+        tmem_st16(t_lane + kColP + half * 32 + c * 16, pk);
+      }
+      l += rowsum;
+      if (threadIdx.x == 0) TRACE(4, j, 4);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&bars[P_FULL]);
+      if (threadIdx.x == 0) TRACE(4, j, 5);
+    }
+    // epilogue: O (accumulated in TMEM), total row sum (both halves), normalise, merge heads, log-sum-exp for the backward
+    mbar_wait(&bars[O_FULL], (nkv - 1) & 1);
+    tc_fence_after();
+    float acc[32];
+    tmem_ld32(t_lane + kColO + half * 32, acc);
+    tc_fence_before();
+    s_max[((nkv & 1) * 2 + half) * kBM + r] = l;                 // the buffer the last tile did not use
+    pair_sync(warp & 3);
+    l += s_max[((nkv & 1) * 2 + (half ^ 1)) * kBM + r];
+    const int q = q0 + r;
+    if (q < N) {
+      const float inv_l = 1.0f / l;
+      uint16_t* dst = o + (((int64_t)b * N + q) * H + h) * kDh + half * 32;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = acc[c * 8 + i] * inv_l;
+        stg_16(dst + c * 8, pack8(t));
+      }
+      if (lse != nullptr && half == 0) lse[((int64_t)b * H + h) * N + q] = m_used + log2f(l);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// =====================================================================================================================
 // backward
 // =====================================================================================================================
 // delta[b,h,n] = sum_d O * dO   (8 lanes per head vector; o / dout are [B,N,H*64])
@@ -409,19 +719,22 @@ constexpr int kDsBufs = VBX_EXP_DSBUF ? 2 : 1;                   // dS^T tiles i
 constexpr uint32_t kDqStageBytes = VBX_EXP_DSBUF ? 16384 : 32768;  // dQ staging: one 32-column half, or both
 constexpr uint32_t kOffK = 0, kOffV = 16384, kOffQ = 32768, kOffdO = kOffQ + kStages * 16384,
                    kOffdST = kOffdO + kStages * 16384, kOffdQ = kOffdST + kDsBufs * 32768, kOffBar = kOffdQ + kDqStageBytes,
-                   kOffStat = kOffBar + 128;  // per compute warp, double buffered: [16 warps][2][32 -lse | 32 delta] f32
+                   kOffStat = kOffBar + 256;  // per compute warp, double buffered: [16 warps][2][32 -lse | 32 delta] f32
 constexpr int kComputeWarps = 16;           // 4 threads per key row: 32 query columns of S^T / dP^T each
-constexpr int kProducerWarp = 16, kMmaWarp = 17, kFlushWarp0 = 18;
-constexpr uint32_t kSmemBytes = kOffStat + kComputeWarps * 2 * 64 * 4;  // 204,928 B: one CTA per SM (TMEM: all 512 columns)
+constexpr int kProducerWarp = 16, kMmaWarp = 17, kFlushWarp0 = 18, kMmaWarpB = 22, kMmaWarpC = 23;  // B, C: VBX_BWD_ISSUERS == 3
+constexpr uint32_t kSmemBytes = kOffStat + kComputeWarps * 2 * 64 * 4;  // ~216 KB: one CTA per SM (TMEM: all 512 columns)
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 enum { KV_FULL = 0, QD_FULL = 1, QD_EMPTY = 4, ST_FULL = 7, ST_FREE = 8, DS_FULL = 9, DQ_FULL = 10, DQ_FREE = 11,
        PT_FREE = 12,   // (VBX_EXP_DSBUF) dV_i has retired: P^T may be overwritten, and so may the dS^T buffer of tile i-1
-       ALL_DONE = 13,  // (VBX_EXP_DSBUF) every GEMM of the CTA has retired
-       NUM_BARS = VBX_EXP_DSBUF ? 14 : 12 };
-static_assert(NUM_BARS * 8 + 4 <= 128, "barrier block");
+       ALL_DONE = 13,  // (VBX_EXP_DSBUF) every dV / dK GEMM of the CTA has retired
+       DSB_FREE = 14,  // (3 issuers) [2]: dK_i AND dQ_i have retired: dS^T buffer i%2 may be overwritten (one barrier per buffer,
+                       // so a waiter is never two phases behind)
+       NUM_BARS = 16 };
+static_assert(NUM_BARS * 8 + 4 <= 256, "barrier block");
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColST = 0, kColDPT = 128, kColDV = 256, kColDK = 320, kColDQ = 384, kColPT = 448;  // P^T: bf16 pairs
-constexpr int kThreads = 704;  // warps 0-15 compute, 16 TMA producer, 17 MMA issuer, 18-21 dQ flush
+constexpr int kThreads = VBX_BWD_ISSUERS == 3 ? 768 : 704;  // warps 0-15 compute, 16 TMA producer, 17 MMA issuer (A), 18-21 dQ flush,
+                                                            // 22-23 MMA issuers B and C
 }  // namespace bwd
 
 // One CTA per (key tile, head, batch); loops over the query tiles.  Everything is computed TRANSPOSED (keys on the
@@ -455,7 +768,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
     mbar_init(&bars[KV_FULL], 1);
     for (int s_ = 0; s_ < kStages; ++s_) {
       mbar_init(&bars[QD_FULL + s_], 1);
-      mbar_init(&bars[QD_EMPTY + s_], 1);
+      mbar_init(&bars[QD_EMPTY + s_], VBX_BWD_ISSUERS == 3 ? 2 : 1);   // 3 issuers: warp A's and warp B's GEMMs both read the stage
     }
     mbar_init(&bars[ST_FULL], 1);
     mbar_init(&bars[ST_FREE], kComputeWarps * 32);
@@ -466,6 +779,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
       mbar_init(&bars[PT_FREE], 1);
       mbar_init(&bars[ALL_DONE], 1);
     }
+    mbar_init(&bars[DSB_FREE], 2);
+    mbar_init(&bars[DSB_FREE + 1], 2);
     fence_barrier_init();
   }
   if (warp == kMmaWarp) {
@@ -495,6 +810,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         tma_load_4d(smem + kOffdO + st * kTileBytes, &mdo, &bars[QD_FULL + st], 0, i * kBM, h, b);
       }
     }
+#if VBX_BWD_ISSUERS == 1
   } else if (warp == kMmaWarp) {
     // warp-uniform control flow, hoisted descriptors (see the forward kernel): only the leader lane issues MMAs / commits
     {
@@ -567,7 +883,100 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         TRACE(0, i, 6);
       }
     }
-  } else if (warp >= kFlushWarp0) {
+#else
+  } else if (warp == kMmaWarp || warp == kMmaWarpB || warp == kMmaWarpC) {
+    // ---- three issuing warps (warp-uniform control flow; the leader lane issues).  tcgen05.mma's of different threads are not
+    // ordered against each other, so EVERY dependency between the three streams goes through an mbarrier, and every barrier
+    // that guards a resource read by two streams counts both commits (QD_EMPTY: A and B; DSB_FREE: B and C). ----
+    constexpr uint32_t idesc_kk = make_idesc(128, 128, false, false);
+    constexpr uint32_t idesc_kmn = make_idesc(128, kDh, false, true);
+    constexpr uint32_t idesc_mnmn = make_idesc(128, kDh, true, true);
+    const bool leader = lane == 0;
+    const int n_qt = VBX_EXP_TAIL ? ((N - (nq - 1) * kBM + 15) & ~15) : kBM;  // GEMM width of the last query tile
+    if (warp == kMmaWarp) {
+      // A: S^T = K Q_i^T, dP^T = V dO_i^T for every tile, as early as the compute warps have pulled tile i-1 out of TMEM
+      const uint64_t dKk = sdesc_k0(smem_u32(smem + kOffK)), dVk = sdesc_k0(smem_u32(smem + kOffV));
+      const uint64_t dQk0 = sdesc_k0(smem_u32(smem + kOffQ)), dOk0 = sdesc_k0(smem_u32(smem + kOffdO));
+      const uint32_t idesc_kk_tail = make_idesc(128, n_qt, false, false);
+      mbar_wait(&bars[KV_FULL], 0);
+      for (int i = 0; i < nq; ++i) {
+        const int st = i % kStages;
+        const uint64_t so = (uint64_t)st * (kTileBytes >> 4);
+        const uint32_t idesc_i = (VBX_EXP_TAIL && i == nq - 1) ? idesc_kk_tail : idesc_kk;
+        TRACE(0, i, 0);
+        mbar_wait(&bars[QD_FULL + st], (i / kStages) & 1);
+        TRACE(0, i, 1);
+        mbar_wait(&bars[ST_FREE], (i & 1) ^ 1);
+        TRACE(0, i, 2);
+        tc_fence_after();
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < kDh / 16; ++k)
+            umma_bf16(tmem_base + kColST, dKk + koff_k(k), dQk0 + so + koff_k(k), idesc_i, k > 0);
+#pragma unroll
+          for (int k = 0; k < kDh / 16; ++k)
+            umma_bf16(tmem_base + kColDPT, dVk + koff_k(k), dOk0 + so + koff_k(k), idesc_i, k > 0);
+          umma_commit(&bars[ST_FULL]);
+          umma_commit(&bars[QD_EMPTY + st]);      // this warp's share: its GEMMs have read Q_i / dO_i
+        }
+        __syncwarp();
+        TRACE(0, i, 3);
+      }
+    } else if (warp == kMmaWarpB) {
+      // B: dV += P^T dO (TS mode), dK += dS^T Q
+      const uint64_t dQmn0 = sdesc_mn0(smem_u32(smem + kOffQ)), dOmn0 = sdesc_mn0(smem_u32(smem + kOffdO));
+      const uint64_t dSk = sdesc_k0(smem_u32(smem + kOffdST));
+      for (int i = 0; i < nq; ++i) {
+        const int st = i % kStages;
+        const uint64_t so = (uint64_t)st * (kTileBytes >> 4);
+        const uint64_t dso = (uint64_t)(i & 1) * (32768 >> 4);
+        mbar_wait(&bars[QD_FULL + st], (i / kStages) & 1);   // (long complete: makes the TMA writes visible to this thread)
+        TRACE(5, i, 0);
+        mbar_wait(&bars[DS_FULL], i & 1);
+        TRACE(5, i, 1);
+        tc_fence_after();
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < kBM / 16; ++k)
+            if (!VBX_EXP_TAIL || i < nq - 1 || k * 16 < n_qt)
+              umma_bf16_ts(tmem_base + kColDV, tmem_base + kColPT + k * 8, dOmn0 + so + koff_mn(k), idesc_kmn, (i > 0) || (k > 0));
+          umma_commit(&bars[PT_FREE]);            // dV_i retired -> P^T (TMEM) may be overwritten
+#pragma unroll
+          for (int k = 0; k < kBM / 16; ++k)
+            if (!VBX_EXP_TAIL || i < nq - 1 || k * 16 < n_qt)
+              umma_bf16(tmem_base + kColDK, dSk + dso + koff_k(k), dQmn0 + so + koff_mn(k), idesc_kmn, (i > 0) || (k > 0));
+          umma_commit(&bars[QD_EMPTY + st]);      // this warp's share
+          umma_commit(&bars[DSB_FREE + (i & 1)]);
+          if (i == nq - 1) umma_commit(&bars[ALL_DONE]);
+        }
+        __syncwarp();
+        TRACE(5, i, 2);
+      }
+    } else {
+      // C: dQ_i = dS K (A = dS^T read MN-major)
+      const uint64_t dKmn = sdesc_mn0(smem_u32(smem + kOffK)), dSmn = sdesc_mn0(smem_u32(smem + kOffdST));
+      mbar_wait(&bars[KV_FULL], 0);
+      for (int i = 0; i < nq; ++i) {
+        const uint64_t dso = (uint64_t)(i & 1) * (32768 >> 4);
+        TRACE(6, i, 0);
+        mbar_wait(&bars[DS_FULL], i & 1);
+        TRACE(6, i, 1);
+        mbar_wait(&bars[DQ_FREE], (i & 1) ^ 1);   // the flush warps have read dQ_{i-1} out of TMEM
+        TRACE(6, i, 2);
+        tc_fence_after();
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < kBN / 16; ++k)
+            umma_bf16(tmem_base + kColDQ, dSmn + dso + koff_mn(k), dKmn + koff_mn(k), idesc_mnmn, k > 0);
+          umma_commit(&bars[DQ_FULL]);
+          umma_commit(&bars[DSB_FREE + (i & 1)]);
+        }
+        __syncwarp();
+        TRACE(6, i, 3);
+      }
+    }
+#endif
+  } else if (warp >= kFlushWarp0 && warp < kFlushWarp0 + 4) {
     // ------------------------------------------------ dQ flush warps -----------------------------------------------
     // dQ_i: TMEM -> registers -> shared -> TMA reduce-add into dq.  Warp w owns query rows [32(w%4), +32): a contiguous,
     // 1024-byte aligned 4 KB slice of each [128 rows][32 fp32] SWIZZLE_128B staging block, reduced with its own 32x32 TMA
@@ -708,6 +1117,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         // shipped: ALL of tile i-1's GEMMs have retired: P^T (TMEM) and the single dS^T tile (shared) may be overwritten.
         // VBX_EXP_DSBUF: dV_{i-1} has retired (so has every GEMM of tile i-2): P^T and dS^T buffer i%2 may be overwritten.
         mbar_wait(&bars[VBX_EXP_DSBUF ? PT_FREE : DQ_FULL], (i - 1) & 1);
+#if VBX_BWD_ISSUERS == 3
+        // separate issuing warps: dV_{i-1} retiring no longer implies that dK_{i-2} / dQ_{i-2} (which read dS^T buffer i%2) have
+        if (i >= 2) mbar_wait(&bars[DSB_FREE + (i & 1)], ((i - 2) >> 1) & 1);
+#endif
         tc_fence_after();
       }
       if (threadIdx.x == 0) TRACE(1, i, 4);
@@ -921,8 +1334,16 @@ extern "C" int vbx_attn_fwd(const uint16_t* q, const uint16_t* k, const uint16_t
   cudaError_t ce = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd::kSmemBytes);
   if (ce != cudaSuccess) return (int)ce;
   dim3 grid((unsigned)((N + kBM - 1) / kBM), (unsigned)H, (unsigned)B);
-  attn_fwd_kernel<<<grid, fwd::kThreads, fwd::kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, key_mask, scale * kLog2e, o, lse, (int)N,
-                                                                       (int)H);
+  static const bool use_v1 = getenv("VBX_ATTN_FWD_V1") != nullptr && getenv("VBX_ATTN_FWD_V1")[0] == '1';   // A/B runs only
+  if (use_v1) {
+    attn_fwd_kernel<<<grid, fwd::kThreads, fwd::kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, key_mask, scale * kLog2e, o, lse, (int)N,
+                                                                         (int)H);
+    return VBX_LAUNCH_RC();
+  }
+  ce = cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd::kSmemBytes);
+  if (ce != cudaSuccess) return (int)ce;
+  attn_fwd2_kernel<<<grid, fwd::kThreads, fwd::kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, key_mask, scale * kLog2e, o, lse, (int)N,
+                                                                        (int)H);
   return VBX_LAUNCH_RC();
 }
 
