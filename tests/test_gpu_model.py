@@ -389,7 +389,8 @@ def test_operand_pack_matches_per_use_casts_and_routes_fp32_gradients(vbx):
     l2, g2, bucket = step(True, True)
     # same bf16 operands; only the 8 gamma/beta projections differ in GEMM algorithm (batched vs one by one): <= one bf16 ulp on
     # a few gamma/beta entries
-    assert l1 == l2 and abs(l0 - l1) <= 2e-4 * abs(l0), (l0, l1, l2)
+    # (l1 vs l2: the masked-MSE numerator is summed with fp32 atomics: equal to ~1e-7, not bitwise)
+    assert abs(l1 - l2) <= 2e-6 * abs(l1) and abs(l0 - l1) <= 2e-4 * abs(l0), (l0, l1, l2)
     assert set(g0) == set(g1) == set(g2)
     for n in g0:
         scale = float(g0[n].abs().max()) + 1e-12

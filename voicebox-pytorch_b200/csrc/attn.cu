@@ -407,6 +407,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
 //   * the two threads of a row agree on the row max through a 64-thread named barrier of just their two warps.
 //   * the tail key tile (N' = 8*128 + 16) runs its S GEMM at N = roundup16(valid), its P V GEMM over valid/16 K-steps, and
 //     32-column chunks that are all padding are skipped outright (no TMEM traffic, no exponentials).
+// EXPERIMENT: the two CTAs of an SM start together and stay in lock step (both in their exponential phase, fighting for the MUFU
+// pipe, then both outside it with the pipe idle: MUFU utilisation 56 % in the round-2 trace).  With VBX_FWD_STAGGER = n > 0 the
+// SECOND first-wave CTA to land on an SM (per-SM arrival counter in device memory, zeroed by the host before the launch) lets its
+// softmax warps spin n clocks before their first tile; every later CTA starts when a predecessor ends and inherits the offset.
+#ifndef VBX_FWD_STAGGER
+#define VBX_FWD_STAGGER 0
+#endif
+__device__ unsigned g_sm_slot[256];
+
 // 64-thread named barrier of the two warps that own the same 32 query rows (ids 2..5; literal ids so that ptxas does not
 // reserve all 16 hardware barriers for the CTA)
 VBX_DEVINL void pair_sync(int quarter) {
@@ -460,6 +469,16 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
+  if (VBX_FWD_STAGGER > 0 && threadIdx.x == 32) {
+    const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    unsigned slot = 0;
+    if (lin < 2u * kNumSM) {   // first wave only
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      slot = atomicAdd(&g_sm_slot[smid & 255u], 1u) & 1u;
+    }
+    tmem_slot[1] = slot;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -485,7 +504,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
       }
     }
   } else if (warp == 9) {
-    // ------------------------------------------------ MMA issuer --------------------------------------------------
+    // ------------------------------------------------ MMA issuer (v2) ---------------------------------------------
     constexpr uint32_t idesc_s = make_idesc(kBM, kBN, false, false);  // S = Q K^T      (both K-major)
     constexpr uint32_t idesc_o = make_idesc(kBM, kDh, false, true);   // O += P V       (V is MN-major: [keys][d])
     const uint64_t dQ = sdesc_k0(smem_u32(smem + kOffQ));
@@ -539,6 +558,11 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     const int r = (warp & 3) * 32 + lane;       // query row of the tile == TMEM lane
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     float m_used = -FLT_MAX, l = 0.f;           // max the exponentials are taken against; partial row sum of this half
+    if (VBX_FWD_STAGGER > 0 && tmem_slot[1] != 0u) {   // second CTA of this SM: start half a tile period late
+      const long long t0 = clock64();
+      while (clock64() - t0 < (long long)VBX_FWD_STAGGER) {
+      }
+    }
 
     for (int j = 0; j < nkv; ++j) {
       const int k0 = j * kBN;
@@ -1342,6 +1366,11 @@ extern "C" int vbx_attn_fwd(const uint16_t* q, const uint16_t* k, const uint16_t
   }
   ce = cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd::kSmemBytes);
   if (ce != cudaSuccess) return (int)ce;
+  if (VBX_FWD_STAGGER > 0) {   // per-SM arrival counters of the stagger experiment (library-owned static device memory)
+    void* slots = nullptr;
+    if ((ce = cudaGetSymbolAddress(&slots, g_sm_slot)) != cudaSuccess) return (int)ce;
+    if ((ce = cudaMemsetAsync(slots, 0, sizeof(unsigned) * 256, (cudaStream_t)stream)) != cudaSuccess) return (int)ce;
+  }
   attn_fwd2_kernel<<<grid, fwd::kThreads, fwd::kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, key_mask, scale * kLog2e, o, lse, (int)N,
                                                                         (int)H);
   return VBX_LAUNCH_RC();

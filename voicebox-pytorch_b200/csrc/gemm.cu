@@ -15,6 +15,8 @@
 //   warps 2-5  epilogue: tcgen05.ld the accumulator (one row per thread), bias / GELU in registers, bf16 tiles staged through a
 //              private 4 KB shared-memory slice per warp in the SWIZZLE_128B pattern and written with TMA stores (clipped at the
 //              tensor edges by the tensor map), overlapped with the next tile's main loop through the second accumulator.
+#include <cstdlib>
+
 #include "umma.cuh"
 
 namespace vbx {
@@ -45,6 +47,30 @@ VBX_DEVINL void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int 
                : "memory");
 }
 VBX_DEVINL void tma_wait_group_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// one box from global memory into the SAME shared-memory offset of every CTA of the cluster named in cta_mask; each destination
+// CTA's mbarrier (same offset) receives the complete_tx
+VBX_DEVINL void tma_load_2d_multicast(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+// arrive (when all prior tcgen05 ops of this thread have completed) on the mbarrier at this offset in every CTA of cta_mask
+VBX_DEVINL void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+VBX_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+VBX_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 
 // 32 packed bf16 pairs (64 columns of this thread's row) -> this warp's [32 rows][128 B] SWIZZLE_128B slice -> one TMA store.
 // `slice` alternates between the two staging blocks: before it is overwritten, the store issued two blocks ago (the last one
@@ -63,12 +89,19 @@ VBX_DEVINL void store_block(uint8_t* slice, const uint32_t (&pk)[32], const CUte
   }
 }
 
+VBX_DEVINL float bf16_to_float(uint16_t v) { return __uint_as_float((uint32_t)v << 16); }
 VBX_DEVINL uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 t = f2bf(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
-// bias[col .. col+32) (bf16) -> fp32; all threads of the CTA read the same addresses (L1 broadcast)
-VBX_DEVINL void load_bias32(const uint16_t* bias, int col, float (&b)[32]) {
+// bias[col .. col+32) (bf16) -> fp32; all threads of the CTA read the same addresses (L1 broadcast).  Columns at or beyond
+// n_cols (clipped by the TMA store anyway) read the last valid entry: nothing is fetched out of bounds for any N % 8 == 0.
+VBX_DEVINL void load_bias32(const uint16_t* bias, int col, int n_cols, float (&b)[32]) {
+  if (col + 32 > n_cols) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) b[i] = bf16_to_float(bias[min(col + i, n_cols - 1)]);
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float t[8];
@@ -81,7 +114,10 @@ VBX_DEVINL void load_bias32(const uint16_t* bias, int col, float (&b)[32]) {
 // mA: A [M, K]; mW: W [N_total, K] (box 128 rows); output maps (box {64, 32}): PLAIN: mO0 = C.  GEGLU: mO0 = value half of h,
 // mO1 = gate half of h, mO2 = g.  n_tiles = column tiles (PLAIN: ceil(N / 256); GEGLU: ceil(Fp / 128)).  gate_row0: row of W
 // where the second 128-row box of a tile starts, relative to the first: PLAIN 128, GEGLU Fp.
-template <int MODE>
+// CLUSTER = 2: two CTAs of a cluster work on vertically adjacent tiles (same W rows).  Each loads ITS activation tile and only
+// HALF of the W tile, multicast into both CTAs' shared memory: W traffic from L2 per tile halves (48 -> 32 KB per k-block).
+// A stage may then only be refilled once BOTH CTAs' MMAs have read it: EMPTY counts two commits, each multicast to both CTAs.
+template <int MODE, int CLUSTER>
 __global__ void __launch_bounds__(gemm::kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW, const __grid_constant__ CUtensorMap mO0,
                  const __grid_constant__ CUtensorMap mO1, const __grid_constant__ CUtensorMap mO2, const uint16_t* __restrict__ bias,
@@ -92,14 +128,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + NUM_BARS * 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (K + kBK - 1) / kBK;
-  const int ntiles = m_tiles * n_tiles;
   constexpr int kColsPerTile = (MODE == PLAIN) ? 256 : 128;   // output columns a tile advances by
+  // work items: CLUSTER == 1: tile t -> (m_blk, n_blk) = (t / n_tiles, t % n_tiles), CTA b takes t = b, b + grid, ...
+  //             CLUSTER == 2: pair p -> m_blk = 2 (p / n_tiles) + rank, n_blk = p % n_tiles, cluster c takes p = c, c + grid/2, ...
+  const int rank = CLUSTER == 2 ? (int)cluster_ctarank() : 0;
+  const int nwork = CLUSTER == 2 ? ((m_tiles + 1) / 2) * n_tiles : m_tiles * n_tiles;
+  const int w0 = CLUSTER == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int wstep = CLUSTER == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+#define VBX_TILE_COORDS(wi)                                                                   \
+  const int m0 = (CLUSTER == 2 ? 2 * ((wi) / n_tiles) + rank : (wi) / n_tiles) * kBM,        \
+            j0 = ((wi) % n_tiles) * kColsPerTile
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&bars[FULL + s], 1);
-      mbar_init(&bars[EMPTY + s], 1);
+      mbar_init(&bars[EMPTY + s], CLUSTER);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars[TFULL + a], 1);
@@ -120,6 +164,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER == 2) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to / arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -127,16 +172,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
     // ------------------------------------------------ TMA producer ------------------------------------------------
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * kBM, j0 = (tile % n_tiles) * kColsPerTile;
+      for (int wi = w0; wi < nwork; wi += wstep) {
+        VBX_TILE_COORDS(wi);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(&bars[EMPTY + s], ((it / kStages) & 1) ^ 1);
           uint8_t* st = smem + s * kStageBytes;
           mbar_arrive_expect_tx(&bars[FULL + s], kStageBytes);
           tma_load_2d(st, &mA, &bars[FULL + s], kb * kBK, m0);
-          tma_load_2d(st + kABytes, &mW, &bars[FULL + s], kb * kBK, j0);
-          tma_load_2d(st + kABytes + kBBytes / 2, &mW, &bars[FULL + s], kb * kBK, second_box_row + j0);
+          if (CLUSTER == 2) {   // this CTA fetches rows [128 rank, +128) of the 256-row W tile for BOTH CTAs
+            tma_load_2d_multicast(st + kABytes + rank * (kBBytes / 2), &mW, &bars[FULL + s], kb * kBK,
+                                  (rank ? second_box_row : 0) + j0, (uint16_t)3);
+          } else {
+            tma_load_2d(st + kABytes, &mW, &bars[FULL + s], kb * kBK, j0);
+            tma_load_2d(st + kABytes + kBBytes / 2, &mW, &bars[FULL + s], kb * kBK, second_box_row + j0);
+          }
         }
       }
     }
@@ -146,7 +196,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
     const uint64_t dA0 = sdesc_k0(smem_u32(smem)), dB0 = sdesc_k0(smem_u32(smem + kABytes));
     const bool leader = lane == 0;
     int it = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+    for (int wi = w0; wi < nwork; wi += wstep, ++tcount) {
       const int acc = tcount & 1;
       mbar_wait(&bars[TEMPTY + acc], ((tcount >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
       tc_fence_after();
@@ -159,7 +209,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
           const uint64_t so = (uint64_t)s * (kStageBytes >> 4);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) umma_bf16(d_tmem, dA0 + so + koff_k(k), dB0 + so + koff_k(k), idesc, (kb | k) != 0);
-          umma_commit(&bars[EMPTY + s]);
+          if (CLUSTER == 2) umma_commit_multicast(&bars[EMPTY + s], (uint16_t)3);
+          else umma_commit(&bars[EMPTY + s]);
           if (kb == nkb - 1) umma_commit(&bars[TFULL + acc]);
         }
         __syncwarp();
@@ -172,9 +223,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
     uint8_t* slice0 = smem + kOffOut + q * 4096;
     uint8_t* slice1 = slice0 + kOutBlockBytes;
     int tcount = 0, blk = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+    for (int wi = w0; wi < nwork; wi += wstep, ++tcount) {
       const int acc = tcount & 1;
-      const int m0 = (tile / n_tiles) * kBM, j0 = (tile % n_tiles) * kColsPerTile;
+      VBX_TILE_COORDS(wi);
       const int row = m0 + q * 32;
       mbar_wait(&bars[TFULL + acc], (tcount >> 1) & 1);
       tc_fence_after();
@@ -192,8 +243,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
               mbar_arrive(&bars[TEMPTY + acc]);
             }
             if (bias != nullptr) {
-              const int col = min(j0 + jj * 64 + hf * 32, n_cols - 32);   // clipped columns are discarded by the store
-              load_bias32(bias, col, b);
+              load_bias32(bias, j0 + jj * 64 + hf * 32, n_cols, b);
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] += b[i];
             }
@@ -216,11 +266,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
               tc_fence_before();
               mbar_arrive(&bars[TEMPTY + acc]);
             }
-            const int col = min(j0 + jj * 64 + hf * 32, n_cols - 32);     // n_cols = Fp here
-            load_bias32(bias, col, b);
+            const int col = j0 + jj * 64 + hf * 32;                       // n_cols = Fp here (a multiple of 32)
+            load_bias32(bias, col, n_cols, b);
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += b[i];
-            load_bias32(bias, n_cols + col, b);
+            load_bias32(bias + n_cols, col, n_cols, b);
 #pragma unroll
             for (int i = 0; i < 32; ++i) g[i] += b[i];
 #pragma unroll
@@ -249,7 +299,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER == 2) cluster_sync_all();   // the peer may still multicast into this CTA's shared memory / arrive on its barriers
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+#undef VBX_TILE_COORDS
 }
 
 // 2-D bf16 tensor map: `inner` contiguous elements per row, `rows` rows `row_pitch` elements apart; box {64, box_rows}, SWIZZLE_128B
@@ -273,14 +325,39 @@ static int launch_gemm(int mode, const uint16_t* a, const uint16_t* w, const uin
   if (mode != PLAIN && (rc = make_tmap_bf16_2d(&mO2, o2, n_cols, M, n_cols, 32)) != VBX_OK) return rc;
   const int m_tiles = (int)((M + kBM - 1) / kBM);
   const int n_tiles = (int)(mode == PLAIN ? (n_cols + 255) / 256 : (n_cols + 127) / 128);
-  const int grid = m_tiles * n_tiles < kNumSM ? m_tiles * n_tiles : kNumSM;
-  cudaStream_t s = (cudaStream_t)stream;
+  // VBX_GEMM_CLUSTER=1 turns the 2-CTA W multicast off (A/B runs); a single-tile-row problem has nothing to share
+  static const bool no_cluster = getenv("VBX_GEMM_CLUSTER") != nullptr && getenv("VBX_GEMM_CLUSTER")[0] == '1';
+  const bool cluster2 = !no_cluster && m_tiles >= 2;
+  int grid;
+  if (cluster2) {
+    const int pairs = ((m_tiles + 1) / 2) * n_tiles;
+    grid = 2 * (pairs < kNumSM / 2 ? pairs : kNumSM / 2);
+  } else {
+    grid = m_tiles * n_tiles < kNumSM ? m_tiles * n_tiles : kNumSM;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster2 ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   cudaError_t ce;
-#define VBX_GEMM_LAUNCH(MODE_, SECOND)                                                                                       \
-  ce = cudaFuncSetAttribute(gemm_bf16_kernel<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);          \
-  if (ce != cudaSuccess) return (int)ce;                                                                                     \
-  gemm_bf16_kernel<MODE_><<<grid, kThreads, kSmemBytes, s>>>(mA, mW, mO0, mO1, mO2, bias, (int)M, (int)n_cols, (int)K, m_tiles,  \
-                                                              n_tiles, (int)(SECOND));
+  const int iM = (int)M, iN = (int)n_cols, iK = (int)K;
+#define VBX_GEMM_LAUNCH(MODE_, SECOND)                                                                                              \
+  {                                                                                                                                  \
+    const int second = (int)(SECOND);                                                                                                \
+    auto kern = cluster2 ? gemm_bf16_kernel<MODE_, 2> : gemm_bf16_kernel<MODE_, 1>;                                                  \
+    ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);                                   \
+    if (ce != cudaSuccess) return (int)ce;                                                                                           \
+    ce = cudaLaunchKernelEx(&cfg, kern, mA, mW, mO0, mO1, mO2, bias, iM, iN, iK, m_tiles, n_tiles, second);                          \
+    if (ce != cudaSuccess) return (int)ce;                                                                                           \
+  }
   if (mode == PLAIN) {
     VBX_GEMM_LAUNCH(PLAIN, 128)
   } else if (mode == GEGLU) {
