@@ -143,6 +143,11 @@ int vbx_ff1_geglu(const uint16_t* x, const uint16_t* w1, const uint16_t* b1, uin
  * Every segment copies a [rows x cols] fp32 matrix into a bf16 matrix of a possibly larger pitch; bytes outside the copied
  * columns / rows are never written (operand buffers are allocated zero-filled once, which is what makes the padding exact). */
 int vbx_pack_bf16(const void* segs, const int64_t* row_start, int64_t n_seg, int64_t total_rows, void* stream);
+/* dst (f32 [rows, cols], row pitch dst_pitch) += src (bf16, row pitch src_pitch): a bf16 weight gradient accumulated into the fp32
+ * master gradient in one pass (replaces autograd's cast + AccumulateGrad add for the weights behind packed operands). */
+int vbx_accum_bf16_2d(float* dst, int64_t dst_pitch, const uint16_t* src, int64_t src_pitch, int64_t rows, int64_t cols, void* stream);
+/* Table form of the same (segment layout of vbx_pack_bf16 with src = bf16, dst = f32): many blocks, one launch. */
+int vbx_accum_bf16_table(const void* segs, const int64_t* row_start, int64_t n_seg, int64_t total_rows, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Fused gradient clip + Adam step over FLAT buffers              replaces accelerator.clip_grad_norm_ + optim.step()

@@ -33,6 +33,8 @@ _SIGNATURES = {
                      _vp],
     'vbx_adam_step': [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _int, _i64, _vp, _vp, _vp],
     'vbx_pack_bf16': [_vp, _vp, _i64, _i64, _vp],
+    'vbx_accum_bf16_2d': [_vp, _i64, _vp, _i64, _i64, _i64, _vp],
+    'vbx_accum_bf16_table': [_vp, _vp, _i64, _i64, _vp],
     'vbx_gemm_bf16': [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
     'vbx_ff1_geglu': [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
     'vbx_umma_selftest': [_vp, _vp, _vp, _int, _vp],

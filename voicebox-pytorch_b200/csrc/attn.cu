@@ -414,11 +414,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
 #ifndef VBX_FWD_STAGGER
 #define VBX_FWD_STAGGER 0
 #endif
+// debug bisection of the v2 forward (bit 0: rescale O on every tile; bit 1: release S only at the end of the tile;
+// bit 2: CTA-wide barrier for the max exchange; bit 3: no tail narrowing)
+#ifndef VBX_V2_DBG
+#define VBX_V2_DBG 0
+#endif
 __device__ unsigned g_sm_slot[256];
 
 // 64-thread named barrier of the two warps that own the same 32 query rows (ids 2..5; literal ids so that ptxas does not
 // reserve all 16 hardware barriers for the CTA)
 VBX_DEVINL void pair_sync(int quarter) {
+#if VBX_V2_DBG & 4
+  named_bar_sync(2, 256);
+  return;
+#endif
   switch (quarter) {
     case 0: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
     case 1: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
@@ -441,7 +450,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kBM, h = blockIdx.y, b = blockIdx.z;
   const int nkv = (N + kBN - 1) / kBN;
-  const int n_tail = (N - (nkv - 1) * kBN + 15) & ~15;        // GEMM width of the last key tile (16 .. 128)
+  const int n_tail = (VBX_V2_DBG & 8) ? kBN : ((N - (nkv - 1) * kBN + 15) & ~15);   // GEMM width of the last key tile (16 .. 128)
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
@@ -579,20 +588,23 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         named_bar_sync(1, 256);
       }
       const int valid = N - k0;                                  // >= 128 except in the tail tile
-      const bool live0 = half * 64 < valid, live1 = half * 64 + 32 < valid;   // warp-uniform: chunk holds at least one key
+      const bool live0 = (VBX_V2_DBG & 8) || half * 64 < valid, live1 = (VBX_V2_DBG & 8) || half * 64 + 32 < valid;   // warp-uniform
       if (threadIdx.x == 0) TRACE(4, j, 0);
       mbar_wait(&bars[S_FULL], j & 1);
       if (threadIdx.x == 0) TRACE(4, j, 1);
       tc_fence_after();
       float s[64];
       {
-        uint32_t* su = reinterpret_cast<uint32_t*>(s);
-        if (live0) tmem_ld32_issue(t_lane + half * 64, su);
-        if (live1) tmem_ld32_issue(t_lane + half * 64 + 32, su + 32);
-        tmem_ld_wait();
+        // one tcgen05.ld + tcgen05.wait::ld per 32 columns (the pattern of tmem_ld32): with two loads in flight behind a single
+        // wait the compiler is free to shuffle the first load's destination registers before the wait, i.e. before the hardware
+        // has written them -- seen on the B200 as sporadic wrong logits (non-repeatable outputs)
+        if (live0) tmem_ld32(t_lane + half * 64, *reinterpret_cast<float(*)[32]>(&s[0]));
+        if (live1) tmem_ld32(t_lane + half * 64 + 32, *reinterpret_cast<float(*)[32]>(&s[32]));
       }
+#if !(VBX_V2_DBG & 2)
       tc_fence_before();
       mbar_arrive(&bars[S_FREE]);                                // this thread's part of S is in registers
+#endif
       // local max over this thread's live columns (log2 domain)
       float mx = -FLT_MAX;
       if (masked_tile) {
@@ -624,7 +636,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         m_used = mx;
       } else {
         const float m_new = fmaxf(m_used, mx);
-        const bool need = (m_new - m_used) > 8.0f;               // lazy: only when p could exceed 2^8
+        const bool need = (VBX_V2_DBG & 1) ? true : (m_new - m_used) > 8.0f;   // lazy: only when p could exceed 2^8
         if (__any_sync(0xffffffffu, need)) {                     // TMEM accesses are warp-wide: lanes that do not need it use 1
           const float alpha = need ? ex2(m_used - m_new) : 1.0f;
           mbar_wait(&bars[O_FULL], (j - 1) & 1);                 // P_{j-1} V_{j-1} has been accumulated
@@ -675,9 +687,19 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         tmem_st16(t_lane + kColP + half * 32 + c * 16, pk);
       }
       l += rowsum;
+      if (j > 0 && !o_ready) {
+        // a warp whose chunks are all padding (tail tile) stored nothing, but it must still OBSERVE this phase of O_FULL: a parity
+        // wait that skips a phase sees the barrier "already flipped" the next time and returns before P V has finished (the
+        // epilogue then read O early: sporadic wrong rows at N' = 8*128 + 16, caught by tools/debug_attn_repeat.py)
+        mbar_wait(&bars[O_FULL], (j - 1) & 1);
+        tc_fence_after();
+      }
       if (threadIdx.x == 0) TRACE(4, j, 4);
       tmem_st_wait();
       tc_fence_before();
+#if VBX_V2_DBG & 2
+      mbar_arrive(&bars[S_FREE]);
+#endif
       mbar_arrive(&bars[P_FULL]);
       if (threadIdx.x == 0) TRACE(4, j, 5);
     }

@@ -56,9 +56,93 @@ __global__ void __launch_bounds__(256) pack_bf16_kernel(const PackSeg* __restric
   }
 }
 
+// dst (f32, row pitch dst_pitch) += src (bf16, row pitch src_pitch) over a [rows x cols] block: the accumulation of a bf16 weight
+// gradient (fast bf16-output library GEMM) into the fp32 master gradient in ONE pass of 10 B / element -- what autograd does in
+// two (cast to fp32: 6 B, then add into .grad: 12 B).
+__global__ void __launch_bounds__(256) accum_bf16_2d_kernel(float* __restrict__ dst, int64_t dst_pitch, const uint16_t* __restrict__ src,
+                                                             int64_t src_pitch, int64_t rows, int64_t cols) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
+    float* d = dst + r * dst_pitch;
+    const uint16_t* s = src + r * src_pitch;
+    if (((reinterpret_cast<uintptr_t>(d) & 15) == 0) && ((reinterpret_cast<uintptr_t>(s) & 7) == 0)) {
+      const int64_t n4 = cols >> 2;
+#pragma unroll 4
+      for (int64_t i = lane; i < n4; i += 32) {
+        const uint2 u = *reinterpret_cast<const uint2*>(s + 4 * i);
+        const float2 a = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), b = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        const uint4 g = ldg_16(d + 4 * i);
+        stg_16(d + 4 * i, make_uint4(__float_as_uint(__uint_as_float(g.x) + a.x), __float_as_uint(__uint_as_float(g.y) + a.y),
+                                     __float_as_uint(__uint_as_float(g.z) + b.x), __float_as_uint(__uint_as_float(g.w) + b.y)));
+      }
+      for (int64_t i = (n4 << 2) + lane; i < cols; i += 32) d[i] += __uint_as_float((uint32_t)s[i] << 16);
+    } else {
+      for (int64_t i = lane; i < cols; i += 32) d[i] += __uint_as_float((uint32_t)s[i] << 16);
+    }
+  }
+}
+
+// table form: segment i adds a bf16 [rows x cols] block into an f32 block (same 6 x int64 layout as PackSeg, with src = bf16 and
+// dst = f32): all 96 gamma/beta weight gradients of a backward in ONE launch
+struct AccumSeg {
+  const uint16_t* src;
+  float* dst;
+  int64_t rows, cols, src_pitch, dst_pitch;
+};
+__global__ void __launch_bounds__(256) accum_bf16_table_kernel(const AccumSeg* __restrict__ segs, const int64_t* __restrict__ row_start,
+                                                                int n_seg) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t total = row_start[n_seg];
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < total; row += warps) {
+    int lo = 0, hi = n_seg;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (row_start[mid] <= row) lo = mid; else hi = mid;
+    }
+    const AccumSeg sg = segs[lo];
+    const int64_t r = row - row_start[lo];
+    float* d = sg.dst + r * sg.dst_pitch;
+    const uint16_t* s = sg.src + r * sg.src_pitch;
+    const int64_t cols = sg.cols;
+    if (((reinterpret_cast<uintptr_t>(d) & 15) == 0) && ((reinterpret_cast<uintptr_t>(s) & 7) == 0)) {
+      const int64_t n4 = cols >> 2;
+#pragma unroll 4
+      for (int64_t i = lane; i < n4; i += 32) {
+        const uint2 u = *reinterpret_cast<const uint2*>(s + 4 * i);
+        const float2 a = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), b = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        const uint4 g = ldg_16(d + 4 * i);
+        stg_16(d + 4 * i, make_uint4(__float_as_uint(__uint_as_float(g.x) + a.x), __float_as_uint(__uint_as_float(g.y) + a.y),
+                                     __float_as_uint(__uint_as_float(g.z) + b.x), __float_as_uint(__uint_as_float(g.w) + b.y)));
+      }
+      for (int64_t i = (n4 << 2) + lane; i < cols; i += 32) d[i] += __uint_as_float((uint32_t)s[i] << 16);
+    } else {
+      for (int64_t i = lane; i < cols; i += 32) d[i] += __uint_as_float((uint32_t)s[i] << 16);
+    }
+  }
+}
+
 }  // namespace vbx
 
 using namespace vbx;
+
+extern "C" int vbx_accum_bf16_table(const void* segs, const int64_t* row_start, int64_t n_seg, int64_t total_rows, void* stream) {
+  VBX_REQUIRE(segs && row_start, VBX_E_NULL);
+  VBX_REQUIRE(n_seg > 0 && n_seg < (1 << 30) && total_rows > 0, VBX_E_SHAPE);
+  static_assert(sizeof(AccumSeg) == 48, "table layout: 6 x int64 per segment");
+  accum_bf16_table_kernel<<<grid_for(total_rows, 8, 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const AccumSeg*>(segs), row_start,
+                                                                                       (int)n_seg);
+  return VBX_LAUNCH_RC();
+}
+
+extern "C" int vbx_accum_bf16_2d(float* dst, int64_t dst_pitch, const uint16_t* src, int64_t src_pitch, int64_t rows, int64_t cols,
+                                 void* stream) {
+  VBX_REQUIRE(dst && src, VBX_E_NULL);
+  VBX_REQUIRE(rows > 0 && cols > 0 && dst_pitch >= cols && src_pitch >= cols, VBX_E_SHAPE);
+  accum_bf16_2d_kernel<<<grid_for(rows, 8, 8), 256, 0, (cudaStream_t)stream>>>(dst, dst_pitch, src, src_pitch, rows, cols);
+  return VBX_LAUNCH_RC();
+}
 
 extern "C" int vbx_pack_bf16(const void* segs, const int64_t* row_start, int64_t n_seg, int64_t total_rows, void* stream) {
   VBX_REQUIRE(segs && row_start, VBX_E_NULL);

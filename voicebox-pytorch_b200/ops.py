@@ -119,9 +119,22 @@ def _route_wgrad(w, ew, dy2, x2):
     """Weight gradient of y = x W_op^T for the fp32 master parameter `w` behind the (possibly padded / row-remapped) operand:
     accumulated in fp32 straight into w.grad when the flat bucket owns it (returns None), else returned as a new fp32 tensor."""
     cols = w.numel() // w.shape[0]
-    xs = x2 if x2.shape[1] == cols else x2[:, :cols]
     sink = _pack.grad_sink(w)
     full = len(ew.maps) == 1 and ew.maps[0][2] == 0 and ew.maps[0][1] == dy2.shape[1]
+    if _pack.accum_mode(dy2.device) == 'kernel':
+        # ONE library GEMM in the operand's own (zero-padded, 16-byte aligned) shape, bf16 out: cuBLASLt's fast path for every
+        # layer.  Then the row blocks / leading columns that exist in the parameter are added into the fp32 gradient in one pass.
+        dw_op = torch.mm(dy2.t(), x2)                                       # [op rows, op cols]
+        if sink is not None:
+            s2 = sink.reshape(w.shape[0], cols)
+            for (p0, cnt, o0) in ew.maps:
+                call('vbx_accum_bf16_2d', s2.data_ptr() + 4 * p0 * cols, cols, dw_op.data_ptr() + 2 * o0 * dw_op.stride(0), dw_op.stride(0),
+                     cnt, cols, stream())
+            _pack.sink_done(w)
+            return None
+        parts = [dw_op[o0:o0 + cnt, :cols] for (p0, cnt, o0) in sorted(ew.maps)]
+        return (parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)).float().reshape(w.shape)
+    xs = x2 if x2.shape[1] == cols else x2[:, :cols]
     if sink is not None:
         s2 = sink.reshape(w.shape[0], cols)
         for (p0, cnt, o0) in ew.maps:
@@ -171,6 +184,9 @@ class _LinearW(torch.autograd.Function):
         return dx, dw, db, None, None
 
 
+_wgrad_buffers = {}   # persistent [K, D, C] bf16 scratch of the batched gamma/beta weight gradient (stable address -> cached table)
+
+
 class _BatchedAffineW(torch.autograd.Function):
     """All K adaptive-norm projections y[k] = cond W[k]^T + b[k] (vp.py:259-260, 273) as ONE batched GEMM on the packed, stacked
     operands W [K, D, C] / bvec [K, D]; returns fp32 [K, B, D].  Backward: dcond as ONE GEMM over the stacked weights, the K
@@ -196,13 +212,25 @@ class _BatchedAffineW(torch.autograd.Function):
             dcond = d16.permute(1, 0, 2).reshape(B, K * D) @ W.reshape(K * D, -1)
         db_all = dout.sum(dim=1)                                                         # fp32 [K, D]
         grads, b_sinks, b_vals = [], [], []
+        w_sinks = [_pack.grad_sink(params[2 * k]) if ctx.needs_input_grad[3 + 2 * k] else None for k in range(K)]
+        table_mode = _pack.accum_mode(dout.device) == 'kernel' and all(s_ is not None for s_ in w_sinks)
+        if table_mode:
+            # all K weight gradients: ONE batched bf16 GEMM into a persistent buffer + ONE table-driven accumulate launch
+            C = cond.shape[1]
+            buf = _wgrad_buffers.get((K, D, C, str(dout.device)))
+            if buf is None:
+                buf = torch.empty((K, D, C), device=dout.device, dtype=BF16)
+                _wgrad_buffers[(K, D, C, str(dout.device))] = buf
+            torch.bmm(d16.transpose(1, 2), cond.unsqueeze(0).expand(K, B, C), out=buf)
+            _pack.accumulate_table(w_sinks, buf, D, C)
         for k in range(K):
             w, b = params[2 * k], params[2 * k + 1]
             gw = gb = None
             if ctx.needs_input_grad[3 + 2 * k]:
-                sink = _pack.grad_sink(w)
-                if sink is not None:
-                    _pack.accumulate_wgrad(sink, d16[k].t(), cond)
+                if table_mode:
+                    _pack.sink_done(w)
+                elif w_sinks[k] is not None:
+                    _pack.accumulate_wgrad(w_sinks[k], d16[k].t(), cond)
                     _pack.sink_done(w)
                 else:
                     gw = _pack.wgrad_fp32(d16[k].t(), cond)

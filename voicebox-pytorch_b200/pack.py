@@ -212,6 +212,12 @@ def _probe_accum_mode(device):
 
 
 def _accum(gview, a_t, b, mode):
+    if mode == 'kernel':
+        # bf16-output library GEMM (the fast path on every GPU) + ONE fused cast-and-accumulate pass (csrc/pack.cu)
+        tmp = torch.mm(a_t, b)
+        assert gview.stride(-1) == 1
+        call('vbx_accum_bf16_2d', ptr_strided(gview), gview.stride(0), ptr(tmp), tmp.stride(0), tmp.shape[0], tmp.shape[1], stream())
+        return
     if mode == 'addmm_out':
         torch.addmm(gview, a_t, b, out_dtype=torch.float32, out=gview)
     elif mode == 'mm32':
@@ -220,20 +226,53 @@ def _accum(gview, a_t, b, mode):
         gview.add_(torch.mm(a_t, b))
 
 
-def accumulate_wgrad(gview, a_t, b):
-    """gview (fp32 [n, k], may be a strided view) += a_t (bf16 [n, m]) @ b (bf16 [m, k])."""
+def accum_mode(device):
+    """'kernel' (default): bf16-output library GEMM + one fused cast-and-accumulate pass (csrc/pack.cu) -- every operand shape and
+    alignment stays on cuBLASLt's fast path; 'addmm_out' / 'mm32': fp32-output GEMMs (measured slower on the B200 for the
+    zero-padded / odd-pitch feed-forward weights, which fall onto a legacy kernel); override with VBX_WGRAD_ACCUM."""
     global _ACCUM_MODE
     if _ACCUM_MODE is None:
-        _ACCUM_MODE = _probe_accum_mode(gview.device)
-    _accum(gview, a_t, b, _ACCUM_MODE)
+        import os
+        _ACCUM_MODE = os.environ.get('VBX_WGRAD_ACCUM') or 'kernel'
+        if _ACCUM_MODE == 'probe':
+            _ACCUM_MODE = _probe_accum_mode(device)
+    return _ACCUM_MODE
+
+
+_tables = {}
+
+
+def accumulate_table(dsts, src, rows, cols):
+    """dsts[k] (f32 [rows, cols] contiguous views) += src[k] (bf16 [K, rows, cols] contiguous) for all k in ONE launch.  The
+    device table is cached on (destination addresses, source address): callers keep `src` in a persistent buffer."""
+    key = (tuple(d.data_ptr() for d in dsts), src.data_ptr(), rows, cols)
+    tab = _tables.get(key)
+    if tab is None:
+        if len(_tables) > 64:
+            _tables.clear()
+        base = src.data_ptr()
+        seg = [(base + 2 * k * rows * cols, d.data_ptr(), rows, cols, cols, cols) for k, d in enumerate(dsts)]
+        start = [k * rows for k in range(len(dsts) + 1)]
+        tab = (torch.tensor(seg, dtype=torch.int64).to(src.device), torch.tensor(start, dtype=torch.int64).to(src.device), start[-1])
+        _tables[key] = tab
+    call('vbx_accum_bf16_table', ptr(tab[0]), ptr(tab[1]), len(dsts), tab[2], stream())
+
+
+def ptr_strided(t):
+    """Device pointer of a row-strided 2-D view (rows need not be contiguous; the last dimension is)."""
+    if not t.is_cuda or t.stride(-1) != 1:
+        raise RuntimeError('expected a CUDA tensor with a contiguous last dimension')
+    return t.data_ptr()
+
+
+def accumulate_wgrad(gview, a_t, b):
+    """gview (fp32 [n, k], may be a strided view) += a_t (bf16 [n, m]) @ b (bf16 [m, k])."""
+    _accum(gview, a_t, b, accum_mode(gview.device))
 
 
 def wgrad_fp32(a_t, b):
     """-> fp32 [n, k] = a_t @ b without a bf16 rounding of the result (used when the parameter has no .grad buffer yet)."""
-    global _ACCUM_MODE
-    if _ACCUM_MODE is None:
-        _ACCUM_MODE = _probe_accum_mode(a_t.device)
-    if _ACCUM_MODE in ('addmm_out', 'mm32'):
+    if accum_mode(a_t.device) in ('addmm_out', 'mm32'):
         return torch.mm(a_t, b, out_dtype=torch.float32)
     return torch.mm(a_t, b).float()
 
