@@ -57,19 +57,44 @@ VBX_DEVINL uint4 pack8(const float f[8]) {
   for (int i = 0; i < 4; ++i) p[i] = f2bf(f[2 * i], f[2 * i + 1]);
   return u;
 }
+// 8 consecutive floats = ONE 32-byte sector.  sm_100 has 256-bit global accesses (LDG.256 / STG.256): one request per sector
+// instead of two 16-byte requests that each touch half of it (the half-sector pattern doubled the L2 <-> SM sector traffic of
+// every fp32 stream in round 1).  Pointers that are only 16-byte aligned fall back to the two-request form.
 VBX_DEVINL void ld8f(const float* p, float f[8]) {
-  uint4 a = ldg_nc_16(p), b = ldg_nc_16(p + 4);
-  f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
-  f[4] = __uint_as_float(b.x); f[5] = __uint_as_float(b.y); f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
+  uint32_t r[8];
+  if ((reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+  } else {
+    const uint4 a = ldg_nc_16(p), b = ldg_nc_16(p + 4);
+    r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[i]);
 }
-VBX_DEVINL void ld8f_rw(const float* p, float f[8]) {
-  uint4 a = ldg_16(p), b = ldg_16(p + 4);
-  f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
-  f[4] = __uint_as_float(b.x); f[5] = __uint_as_float(b.y); f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
+VBX_DEVINL void ld8f_rw(const float* p, float f[8]) {   // without .nc: the same kernel may also write the buffer
+  uint32_t r[8];
+  if ((reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+    asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+  } else {
+    const uint4 a = ldg_16(p), b = ldg_16(p + 4);
+    r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[i]);
 }
 VBX_DEVINL void st8f(float* p, const float f[8]) {
-  stg_16(p, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
-  stg_16(p + 4, make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
+  if ((reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(__float_as_uint(f[0])),
+                 "r"(__float_as_uint(f[1])), "r"(__float_as_uint(f[2])), "r"(__float_as_uint(f[3])), "r"(__float_as_uint(f[4])),
+                 "r"(__float_as_uint(f[5])), "r"(__float_as_uint(f[6])), "r"(__float_as_uint(f[7])));
+  } else {
+    stg_16(p, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+    stg_16(p + 4, make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
+  }
 }
 
 VBX_DEVINL float warp_sum(float v) {

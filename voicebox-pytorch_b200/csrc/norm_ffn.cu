@@ -4,8 +4,39 @@
 
 namespace vbx {
 
+// Element ownership of the row kernels: within chunk c (256 elements) lane l owns the two 4-element groups starting at
+// c*256 + l*4 and c*256 + 128 + l*4.  Every warp-level access is then ONE fully coalesced segment: 512 B for fp32 (16 B per
+// lane), 256 B for bf16 (8 B per lane).  The first version gave each lane 8 CONTIGUOUS elements: its two 16-byte fp32
+// accesses each touched half of 32 different 32-byte sectors, doubling the L2 <-> SM sector traffic of x / dx (0.71-0.75 of
+// the HBM roofline in round 1 although DRAM bytes matched the algorithmic count).
+VBX_DEVINL int grp(int c, int hf, int lane) { return c * 256 + hf * 128 + lane * 4; }
+VBX_DEVINL uint2 ldg_nc_8(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+VBX_DEVINL void stg_8(void* p, uint2 v) {
+  asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y));
+}
+VBX_DEVINL void ld4f(const float* p, float* f, bool rw) {   // rw: the buffer may be written by this kernel (no .nc)
+  const uint4 a = rw ? ldg_16(p) : ldg_nc_16(p);
+  f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
+}
+VBX_DEVINL void st4f(float* p, const float* f) {
+  stg_16(p, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+}
+VBX_DEVINL void ld4h(const uint16_t* p, float* f) {
+  const uint2 u = ldg_nc_8(p);
+  const float2 a = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), b = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+VBX_DEVINL void st4h(uint16_t* p, const float* f) {
+  __nv_bfloat162 a = f2bf(f[0], f[1]), b = f2bf(f[2], f[3]);
+  stg_8(p, make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b)));
+}
+
 // ------------------------------------------------------------------------------------------------------------------
-// residual add + (adaptive) RMSNorm, forward.   One warp per token row; lane l owns elements (c*32+l)*8..+8.
+// residual add + (adaptive) RMSNorm, forward.   One warp per token row; element ownership: grp() above.
 // ------------------------------------------------------------------------------------------------------------------
 template <int C>
 __global__ void __launch_bounds__(256, (C <= 4) ? 4 : 2) adarms_fwd_kernel(const float* __restrict__ x_in, int64_t xbs, int64_t row0,
@@ -23,26 +54,33 @@ __global__ void __launch_bounds__(256, (C <= 4) ? 4 : 2) adarms_fwd_kernel(const
     const float* xi = x_in + b * xbs + (row0 + r) * D;
     float v[C][8];
     float ss = 0.f;
+    const uint16_t* bri = branch != nullptr ? branch + b * xbs + (row0 + r) * D : nullptr;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      const int e = (c * 32 + lane) * 8;
-      if (e < D) {
-        ld8f_rw(xi + e, v[c]);
-        if (branch != nullptr) {
-          float br[8];
-          unpack8(ldg_nc_16(branch + b * xbs + (row0 + r) * D + e), br);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[c][i] += br[i];
+      for (int hf = 0; hf < 2; ++hf) {
+        const int e = grp(c, hf, lane);
+        if (e < D) {
+          ld4f(xi + e, &v[c][hf * 4], true);
+          if (bri != nullptr) {
+            float br[4];
+            ld4h(bri + e, br);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[c][hf * 4 + i] += br[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ss = fmaf(v[c][hf * 4 + i], v[c][hf * 4 + i], ss);
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) ss = fmaf(v[c][i], v[c][i], ss);
       }
     }
     if (x_out != nullptr) {
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const int e = (c * 32 + lane) * 8;
-        if (e < D) st8f(x_out + row * D + e, v[c]);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int e = grp(c, hf, lane);
+          if (e < D) st4f(x_out + row * D + e, &v[c][hf * 4]);
+        }
       }
     }
     ss = warp_sum(ss);
@@ -53,21 +91,24 @@ __global__ void __launch_bounds__(256, (C <= 4) ? 4 : 2) adarms_fwd_kernel(const
     const float* bt = beta ? beta + (per_batch ? b * D : 0) : nullptr;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      const int e = (c * 32 + lane) * 8;
-      if (e < D) {
-        float o[8];
-        const float4 g0 = *reinterpret_cast<const float4*>(g + e), g1 = *reinterpret_cast<const float4*>(g + e + 4);
-        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        if (bt) {
-          const float4 b0 = *reinterpret_cast<const float4*>(bt + e), b1 = *reinterpret_cast<const float4*>(bt + e + 4);
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = fmaf(v[c][i] * scale, gg[i], bb[i]);
-        } else {
+      for (int hf = 0; hf < 2; ++hf) {
+        const int e = grp(c, hf, lane);
+        if (e < D) {
+          float o[4];
+          const float4 g0 = *reinterpret_cast<const float4*>(g + e);
+          const float gg[4] = {g0.x, g0.y, g0.z, g0.w};
+          if (bt) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bt + e);
+            const float bb[4] = {b0.x, b0.y, b0.z, b0.w};
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = v[c][i] * scale * gg[i];
+            for (int i = 0; i < 4; ++i) o[i] = fmaf(v[c][hf * 4 + i] * scale, gg[i], bb[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = v[c][hf * 4 + i] * scale * gg[i];
+          }
+          st4h(h + row * D + e, o);
         }
-        stg_16(h + row * D + e, pack8(o));
       }
     }
   }
@@ -111,20 +152,23 @@ __global__ void __launch_bounds__(256, 2) adarms_bwd_kernel(const float* __restr
     float dot = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      const int e = (c * 32 + lane) * 8;
-      if (e < D) {
-        ld8f(xi + e, xv[c]);
-        unpack8(ldg_nc_16(dh + row * D + e), gv[c]);
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int e = grp(c, hf, lane);
+        if (e < D) {
+          ld4f(xi + e, &xv[c][hf * 4], false);
+          ld4h(dh + row * D + e, &gv[c][hf * 4]);
+        }
       }
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      const int e = (c * 32 + lane) * 8;
-      if (e < D) {
-        const float4 g0 = *reinterpret_cast<const float4*>(g + e), g1 = *reinterpret_cast<const float4*>(g + e + 4);
-        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
+      for (int hf = 0; hf < 2; ++hf) {
+        const int e = grp(c, hf, lane);
+        if (e < D) {
+          const float4 g0 = *reinterpret_cast<const float4*>(g + e);
+          const float gg[4] = {g0.x, g0.y, g0.z, g0.w};
           float4 ag = my_g[(c * 2 + hf) * 32 + lane], ab = my_b[(c * 2 + hf) * 32 + lane];
           float* pg = reinterpret_cast<float*>(&ag);
           float* pb = reinterpret_cast<float*>(&ab);
@@ -133,7 +177,7 @@ __global__ void __launch_bounds__(256, 2) adarms_bwd_kernel(const float* __restr
             const int i = hf * 4 + k;
             pb[k] += gv[c][i];                               // dbeta  += dh
             pg[k] = fmaf(gv[c][i] * xv[c][i], s1, pg[k]);    // dgamma += dh * xhat * sqrt(D)
-            gv[c][i] *= gg[i];                               // dh * gamma
+            gv[c][i] *= gg[k];                               // dh * gamma
             dot = fmaf(gv[c][i], xv[c][i], dot);
           }
           my_g[(c * 2 + hf) * 32 + lane] = ag;
@@ -145,17 +189,21 @@ __global__ void __launch_bounds__(256, 2) adarms_bwd_kernel(const float* __restr
     const float s2 = s1 * rinv * rinv * dot;  // projection on x
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      const int e = (c * 32 + lane) * 8;
-      if (e < D) {
-        float o[8];
-        if (dx_res != nullptr) ld8f(dx_res + row * D + e, o);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float d = fmaf(gv[c][i], s1, -xv[c][i] * s2);
-          o[i] = (dx_res != nullptr) ? o[i] + d : d;
+      for (int hf = 0; hf < 2; ++hf) {
+        const int e = grp(c, hf, lane);
+        if (e < D) {
+          float o[4];
+          if (dx_res != nullptr) ld4f(dx_res + row * D + e, o, false);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = hf * 4 + k;
+            const float d = fmaf(gv[c][i], s1, -xv[c][i] * s2);
+            o[k] = (dx_res != nullptr) ? o[k] + d : d;
+          }
+          st4f(dx + row * D + e, o);
+          if (dbranch != nullptr) st4h(dbranch + row * D + e, o);
         }
-        st8f(dx + row * D + e, o);
-        if (dbranch != nullptr) stg_16(dbranch + row * D + e, pack8(o));
       }
     }
   }
@@ -163,8 +211,8 @@ __global__ void __launch_bounds__(256, 2) adarms_bwd_kernel(const float* __restr
   // cross-warp reduce + one global atomic per column per CTA
   const float* redf = reinterpret_cast<const float*>(red4);
   for (int col = threadIdx.x; col < D; col += blockDim.x) {
-    // element col = (c*32+l)*8 + hf*4 + k  ->  private slot ((c*2+hf)*32 + l)*4 + k
-    const int c = col >> 8, l = (col >> 3) & 31, hf = (col >> 2) & 1, k = col & 3;
+    // element col = c*256 + hf*128 + l*4 + k  ->  private slot ((c*2+hf)*32 + l)*4 + k
+    const int c = col >> 8, hf = (col >> 7) & 1, l = (col >> 2) & 31, k = col & 3;
     const int slot = ((c * 2 + hf) * 32 + l) * 4 + k;
     float sg = 0.f, sb = 0.f;
 #pragma unroll
