@@ -398,8 +398,8 @@ def test_operand_pack_matches_per_use_casts_and_routes_fp32_gradients(vbx):
         scale = float(g0[n].abs().max()) + 1e-12
         assert maxerr(g1[n], g0[n]) <= 1e-2 * scale, (n, maxerr(g1[n], g0[n]), scale)     # bf16 rounding of dW removed
         assert maxerr(g2[n], g1[n]) <= 1e-5 * scale, (n, maxerr(g2[n], g1[n]), scale)     # in-place accumulation == returned
-    for p in bucket.params:
-        assert p.grad.data_ptr() == bucket.flat.data_ptr() + 4 * bucket.offsets[bucket.params.index(p)]
+    for p, off in zip(bucket.params, bucket.offsets):
+        assert p.grad.data_ptr() == bucket.flat.data_ptr() + 4 * off
     # an optimizer update bumps the version counters: the next forward re-packs and the loss changes accordingly
     with torch.no_grad():
         for p in vb.parameters():

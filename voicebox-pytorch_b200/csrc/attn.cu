@@ -419,6 +419,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
 #ifndef VBX_V2_DBG
 #define VBX_V2_DBG 0
 #endif
+#ifndef VBX_ATTN_FWD_DEFAULT
+#define VBX_ATTN_FWD_DEFAULT 2
+#endif
 __device__ unsigned g_sm_slot[256];
 
 // 64-thread named barrier of the two warps that own the same 32 query rows (ids 2..5; literal ids so that ptxas does not
@@ -729,6 +732,317 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 9) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// =====================================================================================================================
+// forward, third generation: TWO query tiles per CTA with strictly alternating exponential phases
+// =====================================================================================================================
+// The v2 trace (profiles/README.md) showed the two co-resident CTAs of an SM in lock step: both in their exponential phase at
+// the same time (each at half the MUFU rate: 2210 clk for 1024 clk of work), then both outside it with the MUFU pipe idle
+// (~1450 clk) -- 56 % MUFU utilisation with MUFU as the binding resource (16 ex2 / clk / SM = 1024 clk per 128 x 128 tile).
+// Two independent CTAs cannot be forced out of phase; two GROUPS inside one CTA can: this kernel runs one CTA per SM, 256 query
+// rows (two 128-row tiles A and B of the same (batch, head)), each with its own 8 softmax warps, its own MMA-issuing warp and
+// its own 256 TMEM columns (S | O | P as in v2), sharing one K/V stream (3-stage TMA ring: K and V are fetched once for both
+// tiles).  A pair of named barriers passes a token between the groups: a group takes the token before its exponentials and
+// hands it over right after them, so the exponential phases strictly alternate (A, B, A, B ...) and everything else a group
+// does per tile -- P store, S load, row max, lazy rescale -- runs while the OTHER group owns the MUFU pipe.
+namespace fwd3 {
+constexpr int kStages = 3;
+constexpr uint32_t kOffQ = 0, kOffK = 32768, kOffV = kOffK + kStages * 16384, kOffBar = kOffV + kStages * 16384,   // 131072
+                   kOffBias = kOffBar + 256, kOffMax = kOffBias + 2 * 2 * kBN * 4, kSmemBytes = kOffMax + 2 * 2 * 2 * kBM * 4;
+enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = 4, V_FULL = 7, V_EMPTY = 10, S_FULL = 13, S_FREE = 15, P_FULL = 17, O_FULL = 19, NUM_BARS = 21 };
+static_assert(NUM_BARS * 8 + 8 <= 256, "barrier block");
+constexpr uint32_t kColO = 128, kColP = 192, kGroupCols = 256;
+constexpr int kProducerWarp = 16, kMmaWarp0 = 17;          // warps 0-7: softmax of tile A, 8-15: tile B, 17 / 18: MMA issuers of A / B
+constexpr int kThreads = 19 * 32;
+}  // namespace fwd3
+
+VBX_DEVINL void bar_sync_id(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+VBX_DEVINL void bar_arrive_id(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+__global__ void __launch_bounds__(fwd3::kThreads, 1)
+attn_fwd3_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
+                 const __grid_constant__ CUtensorMap mv, const uint8_t* __restrict__ key_mask, float scale_log2,
+                 uint16_t* __restrict__ o, float* __restrict__ lse, int N, int H) {
+  using namespace fwd3;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + NUM_BARS * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q_base = blockIdx.x * 2 * kBM;
+  const bool two = q_base + kBM < N;                          // tile B holds at least one real query row
+  const int nkv = (N + kBN - 1) / kBN;
+  const int n_tail = (N - (nkv - 1) * kBN + 15) & ~15;        // GEMM width of the last key tile (16 .. 128)
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    mbar_init(&bars[Q_FULL], 1);
+    for (int s_ = 0; s_ < kStages; ++s_) {
+      mbar_init(&bars[K_FULL + s_], 1);
+      mbar_init(&bars[K_EMPTY + s_], two ? 2 : 1);            // both groups' GEMMs read the stage
+      mbar_init(&bars[V_FULL + s_], 1);
+      mbar_init(&bars[V_EMPTY + s_], two ? 2 : 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&bars[S_FULL + g], 1);
+      mbar_init(&bars[S_FREE + g], 256);
+      mbar_init(&bars[P_FULL + g], 256);
+      mbar_init(&bars[O_FULL + g], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kProducerWarp && lane == 0) {
+    tma_prefetch_desc(&mq);
+    tma_prefetch_desc(&mk);
+    tma_prefetch_desc(&mv);
+  }
+  if (warp == kMmaWarp0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kProducerWarp) {
+    // ------------------------------------------------ TMA producer ------------------------------------------------
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars[Q_FULL], (two ? 2u : 1u) * kTileBytes);
+      tma_load_4d(smem + kOffQ, &mq, &bars[Q_FULL], 0, q_base, h, b);
+      if (two) tma_load_4d(smem + kOffQ + kTileBytes, &mq, &bars[Q_FULL], 0, q_base + kBM, h, b);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j % kStages;
+        const uint32_t ph = ((j / kStages) & 1) ^ 1;
+        if (j + kStages < nkv) {  // warm L2 for the tile after the ring
+          tma_prefetch_l2_4d(&mk, 0, (j + kStages) * kBN, h, b);
+          tma_prefetch_l2_4d(&mv, 0, (j + kStages) * kBN, h, b);
+        }
+        mbar_wait(&bars[K_EMPTY + st], ph);
+        mbar_arrive_expect_tx(&bars[K_FULL + st], kTileBytes);
+        tma_load_4d(smem + kOffK + st * kTileBytes, &mk, &bars[K_FULL + st], 0, j * kBN, h, b);
+        mbar_wait(&bars[V_EMPTY + st], ph);
+        mbar_arrive_expect_tx(&bars[V_FULL + st], kTileBytes);
+        tma_load_4d(smem + kOffV + st * kTileBytes, &mv, &bars[V_FULL + st], 0, j * kBN, h, b);
+      }
+    }
+  } else if (warp >= kMmaWarp0) {
+    // ------------------------------------------------ MMA issuer of group g ---------------------------------------
+    const int g = warp - kMmaWarp0;
+    if (g == 0 || two) {
+      constexpr uint32_t idesc_s = make_idesc(kBM, kBN, false, false);  // S = Q K^T      (both K-major)
+      constexpr uint32_t idesc_o = make_idesc(kBM, kDh, false, true);   // O += P V       (V is MN-major: [keys][d])
+      const uint32_t tb = tmem_base + (uint32_t)g * kGroupCols;
+      const uint64_t dQ = sdesc_k0(smem_u32(smem + kOffQ + g * kTileBytes));
+      const uint64_t dK0 = sdesc_k0(smem_u32(smem + kOffK)), dV0 = sdesc_mn0(smem_u32(smem + kOffV));
+      const bool leader = lane == 0;
+      const uint32_t idesc_s_tail = make_idesc(kBM, n_tail, false, false);
+      mbar_wait(&bars[Q_FULL], 0);
+      auto issue_s = [&](int j) {  // S_j = Q K_j^T
+        const int st = j % kStages;
+        const uint64_t dK = dK0 + (uint64_t)st * (kTileBytes >> 4);
+        const uint32_t idesc_sj = (j == nkv - 1) ? idesc_s_tail : idesc_s;
+        mbar_wait(&bars[K_FULL + st], (j / kStages) & 1);
+        mbar_wait(&bars[S_FREE + g], (j & 1) ^ 1);  // the softmax warps hold S_{j-1} in registers
+        tc_fence_after();
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < kDh / 16; ++k) umma_bf16(tb, dQ + koff_k(k), dK + koff_k(k), idesc_sj, k > 0);
+          umma_commit(&bars[S_FULL + g]);
+          umma_commit(&bars[K_EMPTY + st]);
+        }
+        __syncwarp();
+      };
+      issue_s(0);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j % kStages;
+        const uint64_t dV = dV0 + (uint64_t)st * (kTileBytes >> 4);
+        if (j + 1 < nkv) issue_s(j + 1);
+        mbar_wait(&bars[V_FULL + st], (j / kStages) & 1);
+        if (g == 0) TRACE(3, j, 4);
+        mbar_wait(&bars[P_FULL + g], j & 1);
+        if (g == 0) TRACE(3, j, 5);
+        tc_fence_after();
+        if (leader) {
+          const int ksteps = (j == nkv - 1) ? n_tail / 16 : kBN / 16;
+#pragma unroll
+          for (int k = 0; k < kBN / 16; ++k)
+            if (k < ksteps) umma_bf16_ts(tb + kColO, tb + kColP + k * 8, dV + koff_mn(k), idesc_o, (j > 0) || (k > 0));
+          umma_commit(&bars[O_FULL + g]);
+          umma_commit(&bars[V_EMPTY + st]);
+        }
+        __syncwarp();
+        if (g == 0) TRACE(3, j, 6);
+      }
+    }
+  } else {
+    // ------------------------------------------------ softmax: group g = warp / 8, two threads per query row -------
+    const int g = warp >> 3;
+    if (g == 0 || two) {
+      const int wl = warp & 7;
+      const int half = wl >> 2;                   // which 64 key columns of S / which 32 columns of O
+      const int quarter = wl & 3;                 // TMEM lane quarter (= warp % 4)
+      const int r = quarter * 32 + lane;          // query row of the tile == TMEM lane
+      const int q0 = q_base + g * kBM;
+      const uint32_t t_lane = tmem_base + (uint32_t)g * kGroupCols + ((uint32_t)(quarter * 32) << 16);
+      float* s_bias = reinterpret_cast<float*>(smem + kOffBias) + g * 2 * kBN;     // [2][128] per group
+      float* s_max = reinterpret_cast<float*>(smem + kOffMax) + g * 2 * 2 * kBM;   // [2][2][128] per group
+      const int bias_bar = 1 + g, pair_bar = 3 + g * 4 + quarter, tok_mine = 11 + g, tok_other = 12 - g;
+      uint64_t* bS_FULL = &bars[S_FULL + g];
+      uint64_t* bS_FREE = &bars[S_FREE + g];
+      uint64_t* bP_FULL = &bars[P_FULL + g];
+      uint64_t* bO_FULL = &bars[O_FULL + g];
+      float m_used = -FLT_MAX, l = 0.f;
+      if (two && g == 1) bar_arrive_id(11, 512);  // the token starts with group A
+
+      for (int j = 0; j < nkv; ++j) {
+        const int k0 = j * kBN;
+        const bool masked_tile = (key_mask != nullptr) || (k0 + kBN > N);  // CTA-uniform
+        const float* bias = s_bias + (j & 1) * kBN + half * 64;
+        if (masked_tile) {
+          if (half == 0) {
+            const int key = k0 + r;
+            float v = 0.f;
+            if (key >= N) v = -INFINITY;
+            else if (key_mask != nullptr && !key_mask[(int64_t)b * N + key]) v = -FLT_MAX;
+            s_bias[(j & 1) * kBN + r] = v;
+          }
+          bar_sync_id(bias_bar, 256);
+        }
+        const int valid = N - k0;
+        const bool live0 = half * 64 < valid, live1 = half * 64 + 32 < valid;   // warp-uniform
+        if (threadIdx.x == 0) TRACE(4, j, 0);
+        mbar_wait(bS_FULL, j & 1);
+        if (threadIdx.x == 0) TRACE(4, j, 1);
+        tc_fence_after();
+        float s[64];
+        if (live0) tmem_ld32(t_lane + half * 64, *reinterpret_cast<float(*)[32]>(&s[0]));
+        if (live1) tmem_ld32(t_lane + half * 64 + 32, *reinterpret_cast<float(*)[32]>(&s[32]));
+        tc_fence_before();
+        mbar_arrive(bS_FREE);
+        float mx = -FLT_MAX;
+        if (masked_tile) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            if (!(c ? live1 : live0)) continue;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float bb = bias[c * 32 + i];
+              float t = fmaf(s[c * 32 + i], scale_log2, bb);
+              t = (bb == -INFINITY) ? -INFINITY : t;   // columns >= n_tail hold stale bits
+              s[c * 32 + i] = t;
+              mx = fmaxf(mx, t);
+            }
+          }
+        } else {
+          float m4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+#pragma unroll
+          for (int i = 0; i < 64; ++i) m4[i & 3] = fmaxf(m4[i & 3], s[i]);
+          mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale_log2;
+        }
+        s_max[((j & 1) * 2 + half) * kBM + r] = mx;
+        bar_sync_id(pair_bar, 64);
+        mx = fmaxf(mx, s_max[((j & 1) * 2 + (half ^ 1)) * kBM + r]);
+        bool o_ready = false;
+        if (j == 0) {
+          m_used = mx;
+        } else {
+          const float m_new = fmaxf(m_used, mx);
+          const bool need = (m_new - m_used) > 8.0f;
+          if (__any_sync(0xffffffffu, need)) {
+            const float alpha = need ? ex2(m_used - m_new) : 1.0f;
+            mbar_wait(bO_FULL, (j - 1) & 1);
+            tc_fence_after();
+            o_ready = true;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+              float ov[16];
+              tmem_ld16(t_lane + kColO + half * 32 + c * 16, ov);
+              uint32_t ou[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) ou[i] = __float_as_uint(ov[i] * alpha);
+              tmem_st16(t_lane + kColO + half * 32 + c * 16, ou);
+            }
+            l *= alpha;
+            if (need) m_used = m_new;
+          }
+        }
+        const float neg_m = -m_used;
+        if (threadIdx.x == 0) TRACE(4, j, 2);
+        // ---- exponential phase: this group owns the MUFU pipe between token_wait and token_pass ----
+        if (two) bar_sync_id(tok_mine, 512);
+        if (threadIdx.x == 0) TRACE(4, j, 3);
+        float rowsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (!(c ? live1 : live0)) continue;
+          float* sc = s + c * 32;
+          if (masked_tile) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sc[i] = ex2(sc[i] + neg_m);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sc[i] = VBX_EX2_AT(i, fmaf(sc[i], scale_log2, neg_m));
+          }
+          float r4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r4[i & 3] += sc[i];
+          rowsum += (r4[0] + r4[1]) + (r4[2] + r4[3]);
+          uint32_t pk[16];
+#pragma unroll
+          for (int x = 0; x < 16; ++x) {
+            __nv_bfloat162 t2 = f2bf(sc[2 * x], sc[2 * x + 1]);
+            pk[x] = *reinterpret_cast<uint32_t*>(&t2);
+          }
+          if (j > 0 && !o_ready) {   // P is single-buffered: P_{j-1} V_{j-1} must have read it (long done by now)
+            mbar_wait(bO_FULL, (j - 1) & 1);
+            tc_fence_after();
+            o_ready = true;
+          }
+          tmem_st16(t_lane + kColP + half * 32 + c * 16, pk);
+        }
+        if (two) bar_arrive_id(tok_other, 512);
+        if (threadIdx.x == 0) TRACE(4, j, 4);
+        l += rowsum;
+        if (j > 0 && !o_ready) {   // EVERY warp observes every O_FULL phase (see v2)
+          mbar_wait(bO_FULL, (j - 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bP_FULL);
+        if (threadIdx.x == 0) TRACE(4, j, 5);
+      }
+      if (two && g == 0) bar_sync_id(11, 512);   // absorbs group B's last hand-over
+      // epilogue
+      mbar_wait(bO_FULL, (nkv - 1) & 1);
+      tc_fence_after();
+      float acc[32];
+      tmem_ld32(t_lane + kColO + half * 32, acc);
+      tc_fence_before();
+      s_max[((nkv & 1) * 2 + half) * kBM + r] = l;
+      bar_sync_id(pair_bar, 64);
+      l += s_max[((nkv & 1) * 2 + (half ^ 1)) * kBM + r];
+      const int q = q0 + r;
+      if (q < N) {
+        const float inv_l = 1.0f / l;
+        uint16_t* dst = o + (((int64_t)b * N + q) * H + h) * kDh + half * 32;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float t[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = acc[c * 8 + i] * inv_l;
+          stg_16(dst + c * 8, pack8(t));
+        }
+        if (lse != nullptr && half == 0) lse[((int64_t)b * H + h) * N + q] = m_used + log2f(l);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == fwd3::kMmaWarp0) tmem_dealloc(tmem_base, 512);
 }
 
 // =====================================================================================================================
@@ -1380,10 +1694,22 @@ extern "C" int vbx_attn_fwd(const uint16_t* q, const uint16_t* k, const uint16_t
   cudaError_t ce = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd::kSmemBytes);
   if (ce != cudaSuccess) return (int)ce;
   dim3 grid((unsigned)((N + kBM - 1) / kBM), (unsigned)H, (unsigned)B);
-  static const bool use_v1 = getenv("VBX_ATTN_FWD_V1") != nullptr && getenv("VBX_ATTN_FWD_V1")[0] == '1';   // A/B runs only
-  if (use_v1) {
+  static const int fwd_ver = [] {   // VBX_ATTN_FWD = 1 | 2 | 3 selects the forward kernel generation (A/B runs); default below
+    const char* e = getenv("VBX_ATTN_FWD");
+    if (getenv("VBX_ATTN_FWD_V1") != nullptr && getenv("VBX_ATTN_FWD_V1")[0] == '1') return 1;
+    return (e != nullptr && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : VBX_ATTN_FWD_DEFAULT;
+  }();
+  if (fwd_ver == 1) {
     attn_fwd_kernel<<<grid, fwd::kThreads, fwd::kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, key_mask, scale * kLog2e, o, lse, (int)N,
                                                                          (int)H);
+    return VBX_LAUNCH_RC();
+  }
+  if (fwd_ver == 3) {
+    ce = cudaFuncSetAttribute(attn_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd3::kSmemBytes);
+    if (ce != cudaSuccess) return (int)ce;
+    dim3 grid3((unsigned)((N + 2 * kBM - 1) / (2 * kBM)), (unsigned)H, (unsigned)B);
+    attn_fwd3_kernel<<<grid3, fwd3::kThreads, fwd3::kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, key_mask, scale * kLog2e, o, lse,
+                                                                                 (int)N, (int)H);
     return VBX_LAUNCH_RC();
   }
   ce = cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd::kSmemBytes);

@@ -116,6 +116,8 @@ __global__ void __launch_bounds__(256, (C <= 4) ? 4 : 2) adarms_fwd_kernel(const
 
 // ------------------------------------------------------------------------------------------------------------------
 // backward.  CTA = (batch b, chunk of RC rows); warps stride the chunk; dgamma/dbeta reduced warp -> smem -> global.
+// (lane l owns 8 CONTIGUOUS elements (c*32+l)*8.. here: fp32 rows go through the 256-bit ld8f / st8f, one request per sector;
+//  the grp() mapping of the forward cost 22 % in this kernel -- twice the load / store instructions for the bf16 streams)
 //   g = dh*gamma*sqrt(D);  xh = x/||x||;  dx = (g - xh*(xh.g))/||x|| + dx_res;  dgamma += dh*xh*sqrt(D);  dbeta += dh
 // ------------------------------------------------------------------------------------------------------------------
 // rows per CTA are chosen on the host so that the CTA count is just under a whole number of waves (2 CTAs per SM)
@@ -152,23 +154,20 @@ __global__ void __launch_bounds__(256, 2) adarms_bwd_kernel(const float* __restr
     float dot = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        const int e = grp(c, hf, lane);
-        if (e < D) {
-          ld4f(xi + e, &xv[c][hf * 4], false);
-          ld4h(dh + row * D + e, &gv[c][hf * 4]);
-        }
+      const int e = (c * 32 + lane) * 8;
+      if (e < D) {
+        ld8f(xi + e, xv[c]);
+        unpack8(ldg_nc_16(dh + row * D + e), gv[c]);
       }
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) {
+      const int e = (c * 32 + lane) * 8;
+      if (e < D) {
+        const float4 g0 = *reinterpret_cast<const float4*>(g + e), g1 = *reinterpret_cast<const float4*>(g + e + 4);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        const int e = grp(c, hf, lane);
-        if (e < D) {
-          const float4 g0 = *reinterpret_cast<const float4*>(g + e);
-          const float gg[4] = {g0.x, g0.y, g0.z, g0.w};
+        for (int hf = 0; hf < 2; ++hf) {
           float4 ag = my_g[(c * 2 + hf) * 32 + lane], ab = my_b[(c * 2 + hf) * 32 + lane];
           float* pg = reinterpret_cast<float*>(&ag);
           float* pb = reinterpret_cast<float*>(&ab);
@@ -177,7 +176,7 @@ __global__ void __launch_bounds__(256, 2) adarms_bwd_kernel(const float* __restr
             const int i = hf * 4 + k;
             pb[k] += gv[c][i];                               // dbeta  += dh
             pg[k] = fmaf(gv[c][i] * xv[c][i], s1, pg[k]);    // dgamma += dh * xhat * sqrt(D)
-            gv[c][i] *= gg[k];                               // dh * gamma
+            gv[c][i] *= gg[i];                               // dh * gamma
             dot = fmaf(gv[c][i], xv[c][i], dot);
           }
           my_g[(c * 2 + hf) * 32 + lane] = ag;
@@ -189,21 +188,17 @@ __global__ void __launch_bounds__(256, 2) adarms_bwd_kernel(const float* __restr
     const float s2 = s1 * rinv * rinv * dot;  // projection on x
 #pragma unroll
     for (int c = 0; c < C; ++c) {
+      const int e = (c * 32 + lane) * 8;
+      if (e < D) {
+        float o[8];
+        if (dx_res != nullptr) ld8f(dx_res + row * D + e, o);
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        const int e = grp(c, hf, lane);
-        if (e < D) {
-          float o[4];
-          if (dx_res != nullptr) ld4f(dx_res + row * D + e, o, false);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int i = hf * 4 + k;
-            const float d = fmaf(gv[c][i], s1, -xv[c][i] * s2);
-            o[k] = (dx_res != nullptr) ? o[k] + d : d;
-          }
-          st4f(dx + row * D + e, o);
-          if (dbranch != nullptr) st4h(dbranch + row * D + e, o);
+        for (int i = 0; i < 8; ++i) {
+          const float d = fmaf(gv[c][i], s1, -xv[c][i] * s2);
+          o[i] = (dx_res != nullptr) ? o[i] + d : d;
         }
+        st8f(dx + row * D + e, o);
+        if (dbranch != nullptr) stg_16(dbranch + row * D + e, pack8(o));
       }
     }
   }
@@ -211,8 +206,8 @@ __global__ void __launch_bounds__(256, 2) adarms_bwd_kernel(const float* __restr
   // cross-warp reduce + one global atomic per column per CTA
   const float* redf = reinterpret_cast<const float*>(red4);
   for (int col = threadIdx.x; col < D; col += blockDim.x) {
-    // element col = c*256 + hf*128 + l*4 + k  ->  private slot ((c*2+hf)*32 + l)*4 + k
-    const int c = col >> 8, hf = (col >> 7) & 1, l = (col >> 2) & 31, k = col & 3;
+    // element col = (c*32+l)*8 + hf*4 + k  ->  private slot ((c*2+hf)*32 + l)*4 + k
+    const int c = col >> 8, l = (col >> 3) & 31, hf = (col >> 2) & 1, k = col & 3;
     const int slot = ((c * 2 + hf) * 32 + l) * 4 + k;
     float sg = 0.f, sb = 0.f;
 #pragma unroll
