@@ -397,6 +397,9 @@ def main():
                          'otherwise take SMs from the 1-CTA/SM backward kernels), or chunked all-reduce overlapped with backward')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-sdpa', action='store_true')
+    ap.add_argument('--graph', default=os.environ.get('VBX_STEP_GRAPH', 'off'), choices=['on', 'off'],
+                    help="'on': capture ONE whole training step (zero_grad, forward, backward, all-reduce, clip, Adam) as a CUDA graph and "
+                         "time its replays; falls back to eager launches if the capture fails (reported in config.step_graph)")
     ap.add_argument('--sample-steps', type=int, default=64, help='midpoint solver steps timed in the sampling leg (configs[3]: 64)')
     ap.add_argument('--workload', default='train', choices=['train', 'durpred'],
                     help="'durpred': BASELINE configs[4] -- DurationPredictor dim512 depth10 seq512 batch 128/GPU eval forward, replicas")
@@ -446,10 +449,13 @@ def main():
     bucket = FlatGradBucket(w, overlap=(args.allreduce == 'overlap'))
     bucket.broadcast_parameters(w)
     n_params = sum(p.numel() for p in w.parameters() if p.requires_grad)
+    if args.graph == 'on' and args.optimizer == 'flat':
+        args.optimizer = 'torch'     # FlatAdam keeps the step count on the host (bias corrections would be frozen into the graph)
     if args.optimizer == 'flat':
         opt = vbx.FlatAdam(bucket, lr=3e-4, betas=(0.9, 0.99), eps=1e-8, max_grad_norm=0.5)
     else:
-        opt = torch.optim.Adam([p for p in w.parameters() if p.requires_grad], lr=3e-4, betas=(0.9, 0.99), fused=True)
+        opt = torch.optim.Adam([p for p in w.parameters() if p.requires_grad], lr=3e-4, betas=(0.9, 0.99), fused=True,
+                               capturable=(args.graph == 'on'))
     torch.manual_seed(2 + rank)
     x_host = torch.randn(B, N, D).pin_memory()
     x_dev = x_host.to(dev)
@@ -494,22 +500,69 @@ def main():
         train_step(x_dev)
     torch.cuda.synchronize()
 
-    # ---- device-resident timed region (value) + per-kernel CUDA-event timing -------------------------------------------
+    # ---- optional: the whole step as ONE CUDA graph (same launches, replayed without per-launch host work) ------------------
+    step_graph, graph_note, x_static, static_loss, launches_per_graph = None, 'off', None, None, 0
+    if args.graph == 'on':
+        try:
+            x_static = x_dev.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):       # capture prerequisites: every lazily-built table / cache exists, on a side stream
+                for _ in range(2):
+                    train_step(x_static)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            l0 = vbx._lib.launch_count
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_):
+                static_loss = train_step(x_static)
+            launches_per_graph = vbx._lib.launch_count - l0
+            step_graph, graph_note = g_, 'on'
+            for _ in range(2):
+                g_.replay()
+            torch.cuda.synchronize()
+        except Exception as ex:
+            step_graph, graph_note = None, f'capture failed, eager launches: {ex!r}'[:300]
+            torch.cuda.synchronize()
+
+    def run_step(x):
+        """One training step on batch x (device tensor): graph replay when captured, eager launches otherwise."""
+        if step_graph is None:
+            return train_step(x)
+        if x is not x_static:
+            x_static.copy_(x, non_blocking=True)
+        step_graph.replay()
+        return static_loss
+
+    # ---- device-resident timed region (value) --------------------------------------------------------------------------------
     tracked = ['vbx_attn_fwd', 'vbx_attn_bwd', 'vbx_adarms_fwd', 'vbx_adarms_bwd', 'vbx_geglu_fwd', 'vbx_geglu_bwd',
-               'vbx_qkrope_fwd', 'vbx_qkrope_bwd', 'vbx_convpos_fwd', 'vbx_convpos_bwd']
+               'vbx_qkrope_fwd', 'vbx_qkrope_bwd', 'vbx_convpos_fwd', 'vbx_convpos_bwd', 'vbx_ff1_geglu', 'vbx_pack_bf16',
+               'vbx_accum_bf16_2d', 'vbx_accum_bf16_table', 'vbx_adam_step']
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = vbx._lib.launch_count
-    vbx._lib.profile_start(tracked)
+    if step_graph is None:
+        vbx._lib.profile_start(tracked)     # per-kernel CUDA events inside the timed region (eager launches only)
     torch.cuda.nvtx.range_push('timed')   # `ncu --nvtx --nvtx-include "timed/"` captures exactly this region
-    ms_dev = timed(lambda: train_step(x_dev), args.steps)
+    ms_dev = timed(lambda: run_step(x_static if step_graph is not None else x_dev), args.steps)
     torch.cuda.nvtx.range_pop()
-    prof = vbx._lib.profile_stop()
-    launches = vbx._lib.launch_count - launches0
+    launches = (vbx._lib.launch_count - launches0) if step_graph is None else launches_per_graph * args.steps
     clocks = sampler.stop() if sampler else None
     peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+    ms_eager = None
+    if step_graph is None:
+        prof = vbx._lib.profile_stop()
+    else:
+        # events cannot be placed inside a replayed graph: the per-kernel timings (roofline) come from a second timed region of
+        # the SAME steps launched eagerly, reported as `eager_ms_per_step` next to the graph-replay `ms_per_step`
+        vbx._lib.profile_start(tracked)
+        ms_eager = timed(lambda: train_step(x_dev), args.steps)
+        prof = vbx._lib.profile_stop()
 
     # ---- end-to-end timed region: host batch in, loss out, every step --------------------------------------------------
     def e2e_step():
+        if step_graph is not None:
+            x_static.copy_(x_host, non_blocking=True)
+            return run_step(x_static).item()
         x = x_host.to(dev, non_blocking=True)
         return train_step(x).item()
     if args.profile_only:
@@ -526,16 +579,22 @@ def main():
     # ---- roofline of the dominant hand-written kernel ------------------------------------------------------------------
     Np, T = N + REG, B * (N + REG)
     attn_fl = 4.0 * B * HEADS * Np * Np * 64
+    ms_ref = ms_eager if ms_eager is not None else ms_dev   # the timed region the per-kernel events were taken in
     work = {  # algorithmic FLOPs / bytes per launch
         'vbx_attn_fwd': ('tensor', attn_fl), 'vbx_attn_bwd': ('tensor', 2.5 * attn_fl),
         'vbx_adarms_fwd': ('hbm', T * D * 12.0), 'vbx_adarms_bwd': ('hbm', T * D * 16.0),
         'vbx_geglu_fwd': ('hbm', T * 2752 * 6.0), 'vbx_geglu_bwd': ('hbm', T * 2752 * 10.0),
         'vbx_qkrope_fwd': ('hbm', T * 2048 * 4.0), 'vbx_qkrope_bwd': ('hbm', T * 1024 * (2 + 2 + 2 + 4 + 2 + 2.0)),
         'vbx_convpos_fwd': ('hbm', B * N * D * 6.0), 'vbx_convpos_bwd': ('hbm', B * N * D * 10.0),
+        'vbx_ff1_geglu': ('tensor', 2.0 * T * D * 2 * 2752),
+        'vbx_pack_bf16': ('hbm', n_params * 6.0), 'vbx_adam_step': ('hbm', n_params * 28.0),
     }
     kernels = {}
     for name, (cnt, tot_ms) in prof.items():
         if cnt == 0:
+            continue
+        if name not in work:
+            kernels[name] = dict(launches_per_step=cnt / args.steps, avg_us=tot_ms / cnt * 1e3, ms_per_step=tot_ms / args.steps)
             continue
         kind, units = work[name]
         avg_ms = tot_ms / cnt
@@ -543,7 +602,8 @@ def main():
         peak = peaks['tf_sustained'] if kind == 'tensor' else peaks['hbm']
         kernels[name] = dict(bound=kind, launches_per_step=cnt / args.steps, avg_us=avg_ms * 1e3, ms_per_step=tot_ms / args.steps,
                              achieved=ach, peak=peak, unit='TFLOP/s' if kind == 'tensor' else 'GB/s', frac=ach / peak)
-    dom = max(kernels, key=lambda k: kernels[k]['ms_per_step']) if kernels else None
+    own = [k for k in kernels if 'frac' in kernels[k] and k != 'vbx_ff1_geglu']
+    dom = max(own, key=lambda k: kernels[k]['ms_per_step']) if own else None
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(dom)
@@ -554,7 +614,7 @@ def main():
         k = kernels[dom]
         roofline = dict(kernel=dom, bound=k['bound'], achieved=k['achieved'], peak=k['peak'], unit=k['unit'], frac=k['frac'],
                         traffic=traffic, peak_source=peaks['source'] + (' sustained bf16' if k['bound'] == 'tensor' else ' hbm copy'),
-                        share_of_step=k['ms_per_step'] / (ms_dev / args.steps))
+                        share_of_step=k['ms_per_step'] / (ms_ref / args.steps))
 
     # ---- same-box SDPA baseline for the attention kernels (what the reference's attn_flash=True reaches on this GPU) --------
     sdpa = None
@@ -572,6 +632,7 @@ def main():
     # ---- sampling (BASELINE configs[3]): all 64 midpoint steps, CUDA-graph replay of one captured solver step ---------------
     sample = None
     if not args.no_sample:
+        step_graph = static_loss = x_static = None      # releases the captured step's private memory pool
         del opt
         bucket.flat = None
         for p in w.parameters():
@@ -613,8 +674,9 @@ def main():
                     data='synthetic',
                     config=dict(workload=f'VoiceBox dim{D} depth{args.depth} heads{HEADS} seq{N} (+{REG} register tokens) '
                                          f'batch {B}/GPU, CFM loss fwd+bwd+allreduce+clip+Adam', global_batch=B * world,
-                                seq_len=N, parallelism=f'dp{world}', allreduce=args.allreduce, optimizer=args.optimizer, params=n_params, l2='inputs (268 MB/step) exceed the 126 MB L2',
+                                seq_len=N, parallelism=f'dp{world}', allreduce=args.allreduce, optimizer=args.optimizer, step_graph=graph_note, params=n_params, l2='inputs (268 MB/step) exceed the 126 MB L2',
                                 peak_mem_gib=round(peak_mem, 1)),
+                    eager_ms_per_step=(ms_eager / args.steps if ms_eager is not None else None),
                     e2e=dict(value=e2e_value, unit='frames/s', ms_per_step=ms_e2e / args.steps,
                              h2d_bytes_per_step=x_host.numel() * 4, d2h_bytes_per_step=4),
                     profile_only=bool(args.profile_only), gpu_launches=launches, roofline=roofline, kernels=kernels, sdpa_baseline=sdpa, clocks=clocks,

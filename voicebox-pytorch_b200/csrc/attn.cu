@@ -419,8 +419,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
 #ifndef VBX_V2_DBG
 #define VBX_V2_DBG 0
 #endif
+// Which forward ships: 1 = two-pass softmax, O accumulated in registers (round 1, + tail narrowing); 2 = single pass, O resident in
+// TMEM, lazy rescale; 3 = two query tiles per CTA with alternating exponential phases.  Measured on the same B200 at the bench
+// geometry (B=64, H=16, N'=1040; tools/kbench.py, warm-ups excluded): v1 611.5 us, v2 631.5 us, v3 733 us -- the later
+// generations remove work the trace blamed (second TMEM pass, O round trip, lock-stepped MUFU phases) without getting faster,
+// see DESIGN.md section 5 for what that says about the real limiter.  All three are parity-green and bitwise repeatable.
 #ifndef VBX_ATTN_FWD_DEFAULT
-#define VBX_ATTN_FWD_DEFAULT 2
+#define VBX_ATTN_FWD_DEFAULT 1
 #endif
 __device__ unsigned g_sm_slot[256];
 
