@@ -133,6 +133,14 @@ int vbx_gemm_bf16(const uint16_t* a, const uint16_t* w, const uint16_t* bias, ui
 int vbx_ff1_geglu(const uint16_t* x, const uint16_t* w1, const uint16_t* b1, uint16_t* h, uint16_t* g, int64_t M, int64_t Fp,
                   int64_t K, void* stream);
 
+/* FF2 data gradient + GEGLU backward in one launch (vp.py:337-348, backward):
+ *   dg = dy w2 (never written) ; dh[:, :Fp] = dg * gelu_erf(gate) ; dh[:, Fp:] = dg * value * gelu_erf'(gate) ; db1 += colsum(dh)
+ * dy: bf16 [M, K] (gradient of the feed-forward output); w2t: bf16 [Fp, K] = the second Linear's weight TRANSPOSED and
+ * zero-padded (rows >= F are zero); h: bf16 [M, 2Fp] saved by vbx_ff1_geglu; dh: bf16 [M, 2Fp]; db1: f32 [2Fp], accumulated
+ * with atomics (caller zeroes).  Fp % 64 == 0, K % 8 == 0. */
+int vbx_ff2_dgrad_geglu_bwd(const uint16_t* dy, const uint16_t* w2t, const uint16_t* h, uint16_t* dh, float* db1, int64_t M,
+                            int64_t Fp, int64_t K, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Operand packing                                               replaces the per-use fp32 -> bf16 casts of every Linear weight
  *                                                               and bias under autocast (trainer.py:267; vp.py:259-260, 320,

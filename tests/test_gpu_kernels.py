@@ -407,3 +407,33 @@ def test_tcgen05_ff1_geglu_fused_epilogue(vbx, T, K, Fp):
     assert torch.equal(g2, g)
     val, gate = rbf(h_ref).chunk(2, dim=-1)
     assert rel_err(g, torch.nn.functional.gelu(gate) * val) < 2 ** -6
+
+
+@pytest.mark.parametrize('T,K,Fp', [(300, 128, 192), (129, 64, 64), (1040 * 2, 1024, 2752), (520, 256, 320)])
+def test_tcgen05_ff2_dgrad_with_geglu_backward_epilogue(vbx, T, K, Fp):
+    """csrc/gemm.cu:gemm_geglu_bwd_kernel (vp.py:337-348, backward): dg = dy W2 on tcgen05 with dh = GEGLU'(h) * dg and the FF1
+    bias gradient formed in the epilogue -- against cuBLASLt dgrad GEMM + vbx_geglu_bwd (the pair it replaces) and against the
+    fp32 formula.  dh: 2^-6 of its max (dg carries one bf16 rounding, as in the reference's autocast backward; a differently
+    ordered fp32 accumulation can move that rounding by an ulp); db1 (sums of bf16-rounded dh over T rows): 1e-2 of its max."""
+    torch.manual_seed(13)
+    dy = torch.randn(T, K, device='cuda').to(BF16)
+    w2 = (torch.randn(K, Fp, device='cuda') / math.sqrt(Fp)).to(BF16)          # second Linear's weight [D, Fp]
+    h = (torch.randn(T, 2 * Fp, device='cuda') * 1.5).to(BF16)
+    w2t = w2.t().contiguous()
+    dh = torch.empty_like(h)
+    db = torch.zeros(2 * Fp, device='cuda')
+    vbx._lib.call('vbx_ff2_dgrad_geglu_bwd', dy.data_ptr(), w2t.data_ptr(), h.data_ptr(), dh.data_ptr(), db.data_ptr(), T, Fp, K,
+                  vbx._lib.stream())
+    # the pair it replaces
+    dg = dy @ w2                                                                  # bf16 [T, Fp]
+    dh_pair = torch.empty_like(h)
+    db_pair = torch.zeros(2 * Fp, device='cuda')
+    vbx._lib.call('vbx_geglu_bwd', h.data_ptr(), dg.data_ptr(), dh_pair.data_ptr(), db_pair.data_ptr(), T, Fp, vbx._lib.stream())
+    assert rel_err(dh, dh_pair) < 2 ** -6
+    assert rel_err(db, db_pair) < 1e-2
+    # the formula in fp32
+    hr = h.float().requires_grad_()
+    val, gate = hr.chunk(2, dim=-1)
+    (torch.nn.functional.gelu(gate) * val).backward(rbf(dy.float() @ w2.float()))
+    assert rel_err(dh, hr.grad) < 2 ** -6
+    assert rel_err(db, rbf(hr.grad).sum(dim=0)) < 1e-2

@@ -375,8 +375,9 @@ def test_operand_pack_matches_per_use_casts_and_routes_fp32_gradients(vbx):
         assert torch.equal(bvec[2 * i], n.to_gamma.bias.detach().to(torch.bfloat16))
     assert torch.equal(pk.lookup(vb.to_pred.weight).op, vb.to_pred.weight.detach().to(torch.bfloat16))
 
-    def step(packed, bucketed):
+    def step(packed, bucketed, fused_ff_bwd='1'):
         vbx.modules.PACKED = packed
+        vbx.ops.FUSED_FF_BWD = fused_ff_bwd
         try:
             w.zero_grad(set_to_none=True)
             bucket = FlatGradBucket(w) if bucketed else None
@@ -386,6 +387,7 @@ def test_operand_pack_matches_per_use_casts_and_routes_fp32_gradients(vbx):
             return float(loss), {n: p.grad.clone() for n, p in vb.named_parameters() if p.grad is not None}, bucket
         finally:
             vbx.modules.PACKED = True
+            vbx.ops.FUSED_FF_BWD = '1'
     l0, g0, _ = step(False, False)
     l1, g1, _ = step(True, False)
     l2, g2, bucket = step(True, True)
@@ -400,6 +402,12 @@ def test_operand_pack_matches_per_use_casts_and_routes_fp32_gradients(vbx):
         assert maxerr(g2[n], g1[n]) <= 1e-5 * scale, (n, maxerr(g2[n], g1[n]), scale)     # in-place accumulation == returned
     for p, off in zip(bucket.params, bucket.offsets):
         assert p.grad.data_ptr() == bucket.flat.data_ptr() + 4 * off
+    # the feed-forward block as ONE node (FF2 dgrad + GEGLU backward fused into a tcgen05 epilogue) vs the two-node path
+    l5, g5, _ = step(True, False, fused_ff_bwd='0')
+    assert abs(l5 - l1) <= 2e-6 * abs(l1)
+    for n in g1:
+        scale = float(g1[n].abs().max()) + 1e-12
+        assert maxerr(g5[n], g1[n]) <= 2e-2 * scale, (n, maxerr(g5[n], g1[n]), scale)
     # an optimizer update bumps the version counters: the next forward re-packs and the loss changes accordingly
     with torch.no_grad():
         for p in vb.parameters():

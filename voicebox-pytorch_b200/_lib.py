@@ -37,6 +37,7 @@ _SIGNATURES = {
     'vbx_accum_bf16_table': [_vp, _vp, _i64, _i64, _vp],
     'vbx_gemm_bf16': [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
     'vbx_ff1_geglu': [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
+    'vbx_ff2_dgrad_geglu_bwd': [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
     'vbx_umma_selftest': [_vp, _vp, _vp, _int, _vp],
 }
 

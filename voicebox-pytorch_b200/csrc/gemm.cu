@@ -304,6 +304,228 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
 #undef VBX_TILE_COORDS
 }
 
+// =====================================================================================================================
+// FF2 data-gradient GEMM with the GEGLU backward as its epilogue (vp.py:337-348, backward):
+//   dg = dy W2            [M, Fp]   (A = dy [M, D] K-major;  B = W2^T operand [Fp, D] K-major, zero rows beyond F)
+//   dh[:, :Fp]  = dg * gelu_erf(gate)              dh[:, Fp:] = dg * value * gelu_erf'(gate)          (h = [value | gate], bf16)
+//   db1[c]     += sum over rows of dh[:, c]        (fp32 atomics; the bias gradient of the first Linear)
+// Replaces the library dgrad GEMM *and* the stand-alone geglu_bwd pass (1.83 GB of HBM traffic per layer at cfg3: dg is never
+// written, h is read once, dh is written once).  Same main loop as gemm_bf16_kernel, 3 stages (the staging area doubles), EIGHT
+// epilogue warps: the GEGLU backward costs ~2.5x the forward's math per element, four warps could not drain a 128 x 256
+// accumulator within one tile's main loop.  Warps 2-5 take accumulator columns [0,128), warps 6-9 columns [128,256); both sets
+// cover the four TMEM lane quarters.  Column sums: a 5-step butterfly leaves lane l with the sums of columns 2l, 2l+1 of each
+// 64-column chunk (62 shuffles per 64 values), then one atomic per column per warp.
+// =====================================================================================================================
+namespace gemmb {
+constexpr int kBM = 128, kBN = 256, kBK = 64, kStages = 3;
+constexpr uint32_t kABytes = kBM * kBK * 2, kBBytes = kBN * kBK * 2, kStageBytes = kABytes + kBBytes;
+constexpr uint32_t kOffOut = kStages * kStageBytes;                 // 4 x [128 rows][64 bf16] staging blocks (2 per column half)
+constexpr uint32_t kOutBlockBytes = kBM * 64 * 2;
+constexpr uint32_t kOffBar = kOffOut + 4 * kOutBlockBytes;
+enum { FULL = 0, EMPTY = kStages, TFULL = 2 * kStages, TEMPTY = 2 * kStages + 2, NUM_BARS = 2 * kStages + 4 };
+constexpr uint32_t kSmemBytes = kOffBar + NUM_BARS * 8 + 16;
+static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB)");
+constexpr int kThreads = 320;
+}  // namespace gemmb
+
+// butterfly over the 32 lanes: x[0..N) per lane in -> after the 5 steps lane l holds in x[0], x[1] the sums over all lanes of
+// the original elements 2l and 2l+1  (N = 64)
+VBX_DEVINL void warp_colsum64(float (&x)[64], int lane) {
+#pragma unroll
+  for (int s = 16, n = 64; s >= 1; s >>= 1, n >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (i < n / 2) {
+        const float send = upper ? x[i] : x[i + n / 2];
+        const float keep = upper ? x[i + n / 2] : x[i];
+        x[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+      }
+    }
+  }
+}
+
+template <int CLUSTER>
+__global__ void __launch_bounds__(gemmb::kThreads, 1)
+gemm_geglu_bwd_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW, const __grid_constant__ CUtensorMap mO0,
+                      const __grid_constant__ CUtensorMap mO1, const uint16_t* __restrict__ h, float* __restrict__ db, int M, int Fp, int K,
+                      int m_tiles, int n_tiles) {
+  using namespace gemmb;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + NUM_BARS * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (K + kBK - 1) / kBK;
+  const int rank = CLUSTER == 2 ? (int)cluster_ctarank() : 0;
+  const int nwork = CLUSTER == 2 ? ((m_tiles + 1) / 2) * n_tiles : m_tiles * n_tiles;
+  const int w0 = CLUSTER == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int wstep = CLUSTER == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+#define VBX_TILE_COORDS(wi)                                                                   \
+  const int m0 = (CLUSTER == 2 ? 2 * ((wi) / n_tiles) + rank : (wi) / n_tiles) * kBM,        \
+            j0 = ((wi) % n_tiles) * kBN
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&bars[FULL + s], 1);
+      mbar_init(&bars[EMPTY + s], CLUSTER);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&bars[TFULL + a], 1);
+      mbar_init(&bars[TEMPTY + a], 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mA);
+    tma_prefetch_desc(&mW);
+    tma_prefetch_desc(&mO0);
+    tma_prefetch_desc(&mO1);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CLUSTER == 2) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int wi = w0; wi < nwork; wi += wstep) {
+        VBX_TILE_COORDS(wi);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kStages;
+          mbar_wait(&bars[EMPTY + s], ((it / kStages) & 1) ^ 1);
+          uint8_t* st = smem + s * kStageBytes;
+          mbar_arrive_expect_tx(&bars[FULL + s], kStageBytes);
+          tma_load_2d(st, &mA, &bars[FULL + s], kb * kBK, m0);
+          if (CLUSTER == 2) {
+            tma_load_2d_multicast(st + kABytes + rank * (kBBytes / 2), &mW, &bars[FULL + s], kb * kBK, rank * 128 + j0, (uint16_t)3);
+          } else {
+            tma_load_2d(st + kABytes, &mW, &bars[FULL + s], kb * kBK, j0);
+            tma_load_2d(st + kABytes + kBBytes / 2, &mW, &bars[FULL + s], kb * kBK, 128 + j0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc(kBM, kBN, false, false);
+    const uint64_t dA0 = sdesc_k0(smem_u32(smem)), dB0 = sdesc_k0(smem_u32(smem + kABytes));
+    const bool leader = lane == 0;
+    int it = 0, tcount = 0;
+    for (int wi = w0; wi < nwork; wi += wstep, ++tcount) {
+      const int acc = tcount & 1;
+      mbar_wait(&bars[TEMPTY + acc], ((tcount >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * kBN;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % kStages;
+        mbar_wait(&bars[FULL + s], (it / kStages) & 1);
+        tc_fence_after();
+        if (leader) {
+          const uint64_t so = (uint64_t)s * (kStageBytes >> 4);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) umma_bf16(d_tmem, dA0 + so + koff_k(k), dB0 + so + koff_k(k), idesc, (kb | k) != 0);
+          if (CLUSTER == 2) umma_commit_multicast(&bars[EMPTY + s], (uint16_t)3);
+          else umma_commit(&bars[EMPTY + s]);
+          if (kb == nkb - 1) umma_commit(&bars[TFULL + acc]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue: 8 warps ---------------------------------------------
+    const int q = warp & 3;                                   // TMEM lane quarter
+    const int grp = (warp - 2) >> 2;                          // 0: accumulator columns [0,128), 1: [128,256)
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint8_t* slice0 = smem + kOffOut + (grp * 2) * kOutBlockBytes + q * 4096;
+    uint8_t* slice1 = slice0 + kOutBlockBytes;
+    int tcount = 0, blk = 0;
+    for (int wi = w0; wi < nwork; wi += wstep, ++tcount) {
+      const int acc = tcount & 1;
+      VBX_TILE_COORDS(wi);
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < M;
+      mbar_wait(&bars[TFULL + acc], (tcount >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_acc = t_lane + (uint32_t)acc * kBN + grp * 128;
+#pragma unroll 1
+      for (int jj = 0; jj < 2; ++jj) {
+        const int col = j0 + grp * 128 + jj * 64;             // first dg / value column of this 64-column chunk
+        const bool col_ok = col < Fp;                         // Fp % 64 == 0: a chunk is entirely inside or entirely outside
+        float sv[64], sg[64];                                 // bf16-rounded dh values of this row: value half, gate half
+        if (col_ok) {
+          const uint16_t* hp = h + (int64_t)(row_ok ? row : 0) * 2 * Fp + col;   // this row's value / gate entries of h
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint4 hv[4], hg[4];                                 // 32 value + 32 gate entries: one 64-byte half line each
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              hv[i] = row_ok ? ldg_nc_16(hp + hf * 32 + 8 * i) : make_uint4(0, 0, 0, 0);
+              hg[i] = row_ok ? ldg_nc_16(hp + Fp + hf * 32 + 8 * i) : make_uint4(0, 0, 0, 0);
+            }
+            float d[32];
+            tmem_ld32(t_acc + jj * 64 + hf * 32, d);
+            if (jj == 1 && hf == 1) {                          // last read of this accumulator half by this thread
+              tc_fence_before();
+              mbar_arrive(&bars[TEMPTY + acc]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float v8[8], g8[8];
+              unpack8(hv[i], v8);
+              unpack8(hg[i], g8);
+#pragma unroll
+              for (int x = 0; x < 8; ++x) {
+                const int c = hf * 32 + i * 8 + x;
+                // dg is a bf16 tensor in the reference's autocast backward: round it before it is used
+                const float dd = __bfloat162float(__float2bfloat16_rn(d[i * 8 + x]));
+                float e;
+                const float cdf = normal_cdf(g8[x], e);
+                const float dval = dd * (g8[x] * cdf);
+                const float dgate = dd * v8[x] * fmaf(g8[x] * 0.3989422804014327f, e, cdf);
+                sv[c] = __bfloat162float(__float2bfloat16_rn(dval));
+                sg[c] = __bfloat162float(__float2bfloat16_rn(dgate));
+              }
+            }
+          }
+          uint32_t pv[32], pg[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            pv[i] = pack_bf16x2(sv[2 * i], sv[2 * i + 1]);
+            pg[i] = pack_bf16x2(sg[2 * i], sg[2 * i + 1]);
+          }
+          store_block((blk & 1) ? slice1 : slice0, pv, &mO0, col, m0 + q * 32, lane);
+          ++blk;
+          store_block((blk & 1) ? slice1 : slice0, pg, &mO1, col, m0 + q * 32, lane);
+          ++blk;
+          // bias gradient of the first Linear: column sums of dh over this warp's 32 rows (rows >= M contribute zeros: their
+          // dy rows were zero-filled by TMA)
+          warp_colsum64(sv, lane);
+          warp_colsum64(sg, lane);
+          atomicAdd(db + col + 2 * lane, sv[0]);
+          atomicAdd(db + col + 2 * lane + 1, sv[1]);
+          atomicAdd(db + Fp + col + 2 * lane, sg[0]);
+          atomicAdd(db + Fp + col + 2 * lane + 1, sg[1]);
+        } else if (jj == 1) {                                   // (warp-uniform) nothing to do, but the accumulator must be released
+          tc_fence_before();
+          mbar_arrive(&bars[TEMPTY + acc]);
+        }
+      }
+    }
+    if (lane == 0) tma_wait_group0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CLUSTER == 2) cluster_sync_all();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+#undef VBX_TILE_COORDS
+}
+
 // 2-D bf16 tensor map: `inner` contiguous elements per row, `rows` rows `row_pitch` elements apart; box {64, box_rows}, SWIZZLE_128B
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t inner, int64_t rows, int64_t row_pitch, int box_rows);
 
@@ -385,4 +607,48 @@ extern "C" int vbx_ff1_geglu(const uint16_t* x, const uint16_t* w1, const uint16
   VBX_REQUIRE(VBX_ALIGNED16(x) && VBX_ALIGNED16(w1) && VBX_ALIGNED16(b1) && VBX_ALIGNED16(g) && (!h || VBX_ALIGNED16(h)), VBX_E_ALIGN);
   if (h != nullptr) return launch_gemm(gemm::GEGLU, x, w1, b1, h, 2 * Fp, h + Fp, g, M, Fp, K, 2 * Fp, stream);
   return launch_gemm(gemm::GEGLU_NOH, x, w1, b1, g, Fp, nullptr, g, M, Fp, K, 2 * Fp, stream);
+}
+
+extern "C" int vbx_ff2_dgrad_geglu_bwd(const uint16_t* dy, const uint16_t* w2t, const uint16_t* h, uint16_t* dh, float* db1, int64_t M,
+                                       int64_t Fp, int64_t K, void* stream) {
+  using namespace gemmb;
+  VBX_REQUIRE(dy && w2t && h && dh && db1, VBX_E_NULL);
+  VBX_REQUIRE(M > 0 && Fp >= 64 && K > 0 && M < (1ll << 31) && Fp < (1ll << 30) && K < (1ll << 31) && Fp % 64 == 0 && K % 8 == 0,
+              VBX_E_SHAPE);
+  VBX_REQUIRE(VBX_ALIGNED16(dy) && VBX_ALIGNED16(w2t) && VBX_ALIGNED16(h) && VBX_ALIGNED16(dh), VBX_E_ALIGN);
+  CUtensorMap mA, mW, mO0, mO1;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&mA, dy, K, M, K, kBM)) != VBX_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&mW, w2t, K, Fp, K, 128)) != VBX_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&mO0, dh, Fp, M, 2 * Fp, 32)) != VBX_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&mO1, dh + Fp, Fp, M, 2 * Fp, 32)) != VBX_OK) return rc;
+  const int m_tiles = (int)((M + kBM - 1) / kBM), n_tiles = (int)((Fp + kBN - 1) / kBN);
+  static const bool no_cluster = getenv("VBX_GEMM_CLUSTER") != nullptr && getenv("VBX_GEMM_CLUSTER")[0] == '1';
+  const bool cluster2 = !no_cluster && m_tiles >= 2;
+  int grid;
+  if (cluster2) {
+    const int pairs = ((m_tiles + 1) / 2) * n_tiles;
+    grid = 2 * (pairs < kNumSM / 2 ? pairs : kNumSM / 2);
+  } else {
+    grid = m_tiles * n_tiles < kNumSM ? m_tiles * n_tiles : kNumSM;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster2 ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  auto kern = cluster2 ? gemm_geglu_bwd_kernel<2> : gemm_geglu_bwd_kernel<1>;
+  cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  if (ce != cudaSuccess) return (int)ce;
+  const int iM = (int)M, iF = (int)Fp, iK = (int)K;
+  ce = cudaLaunchKernelEx(&cfg, kern, mA, mW, mO0, mO1, h, db1, iM, iF, iK, m_tiles, n_tiles);
+  if (ce != cudaSuccess) return (int)ce;
+  return VBX_LAUNCH_RC();
 }

@@ -290,6 +290,9 @@ def _ff_branch(ff, h):
     if pk is not None:
         ew, eb = pk.lookup(lin1.weight), pk.lookup(lin1.bias)
         if ew is not None and eb is not None:
+            y = ops.feed_forward_packed(h, lin1, lin2, pk, ff.__dict__.get('_vbx_w2t'))   # training: one node, fused epilogues
+            if y is not None:
+                return y
             g = ops.linear_geglu_packed(h, lin1.weight, lin1.bias, ew, eb)
             return ops.linear(g, lin2.weight, lin2.bias)
     f = lin2.in_features

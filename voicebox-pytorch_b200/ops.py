@@ -464,6 +464,57 @@ def _ff1_nograd(x, w_op, b_op):
     return geglu(F.linear(x, w_op, b_op))
 
 
+# FF2 dgrad + GEGLU backward as ONE tcgen05 kernel (csrc/gemm.cu) instead of cuBLASLt dgrad GEMM + geglu_bwd; VBX_FUSED_FF_BWD=0
+# restores the pair
+FUSED_FF_BWD = _os.environ.get('VBX_FUSED_FF_BWD', '1')
+
+
+class _FeedForwardPacked(torch.autograd.Function):
+    """The whole feed-forward block y = W2 GEGLU(W1 x + b1) + b2 (vp.py:342-349) on packed operands, as one autograd node:
+    forward = tcgen05 FF1 GEMM with the bias + GEGLU epilogue (h and g written once) + library FF2 GEMM;
+    backward = library wgrad GEMMs (accumulated into the fp32 masters, pack.py) + ONE tcgen05 kernel for the FF2 data gradient
+    with the GEGLU backward and the FF1 bias gradient as its epilogue (dg is never written, h is read once) + library FF1 dgrad."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, e1, eb1, e2, eb2, w2t):
+        shp = x.shape
+        x2 = _c(x.reshape(-1, shp[-1]))
+        h, g = ff1_geglu(x2, e1.op, eb1.op, True)
+        y = F.linear(g, e2.op, eb2.op)
+        ctx.save_for_backward(x2, h, g)
+        ctx.misc = (shp, w1, b1, w2, b2, e1, eb1, e2, eb2, w2t)
+        return y.reshape(shp[:-1] + (y.shape[-1],))
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, h, g = ctx.saved_tensors
+        shp, w1, b1, w2, b2, e1, eb1, e2, eb2, w2t = ctx.misc
+        dy2 = _c(dy.reshape(-1, dy.shape[-1]))
+        T, two_fp = h.shape
+        fp = two_fp // 2
+        dw2 = _route_wgrad(w2, e2, dy2, g) if ctx.needs_input_grad[3] else None
+        db2 = _route_bgrad(b2, eb2, dy2.sum(dim=0, dtype=torch.float32)) if ctx.needs_input_grad[4] else None
+        dh = torch.empty_like(h)
+        db1_op = torch.zeros((two_fp,), device=h.device, dtype=torch.float32)
+        call('vbx_ff2_dgrad_geglu_bwd', ptr(dy2), ptr(w2t), ptr(h), ptr(dh), ptr(db1_op), T, fp, dy2.shape[1], stream())
+        dx = (dh @ e1.op).reshape(shp) if ctx.needs_input_grad[0] else None
+        dw1 = _route_wgrad(w1, e1, dh, x2) if ctx.needs_input_grad[1] else None
+        db1 = _route_bgrad(b1, eb1, db1_op) if ctx.needs_input_grad[2] else None
+        return dx, dw1, db1, dw2, db2, None, None, None, None, None
+
+
+def feed_forward_packed(x, lin1, lin2, pk, w2t):
+    """-> FF(x) through _FeedForwardPacked when everything it needs is packed and enabled, else None (caller takes the two-node path)."""
+    if FUSED_FF_BWD != '1' or FUSED_FF1 != '1' or w2t is None or not torch.is_grad_enabled():
+        return None
+    e1, eb1, e2, eb2 = pk.lookup(lin1.weight), pk.lookup(lin1.bias), pk.lookup(lin2.weight), pk.lookup(lin2.bias)
+    if None in (e1, eb1, e2, eb2) or (e1.op.shape[0] // 2) % 64 != 0 or x.shape[-1] % 8 != 0 or lin2.out_features % 8 != 0:
+        return None
+    if not (x.requires_grad or lin1.weight.requires_grad or lin2.weight.requires_grad):
+        return None
+    return _FeedForwardPacked.apply(x, lin1.weight, lin1.bias, lin2.weight, lin2.bias, e1, eb1, e2, eb2, w2t)
+
+
 def linear_geglu_packed(x, w, b, ew, eb):
     """Same on the packed operands ew / eb of the fp32 master parameters w [2F, D], b [2F] (pack.py)."""
     if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or b.requires_grad):

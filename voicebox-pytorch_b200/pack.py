@@ -38,6 +38,7 @@ class OperandPack:
         self._row_start = None
         self._sig = None
         self._total_rows = 0
+        self.post_copies = []    # (dst, src_view): derived operands refreshed right after the pack launch (e.g. transposes)
 
     # ---- registration ---------------------------------------------------------------------------------------------
     def add(self, param, op_shape=None, row_map=None, op=None, op_offset=0):
@@ -92,6 +93,8 @@ class OperandPack:
             self._build_table()
         with torch.cuda.device(self.device):
             call('vbx_pack_bf16', ptr(self._table), ptr(self._row_start), self._table.shape[0], self._total_rows, stream())
+            for dst, src in self.post_copies:
+                dst.copy_(src)
         self._sig = sig
         return True
 
@@ -154,6 +157,11 @@ def build_for_transformer(pack, tr):
             pack.add(lin1.bias, op_shape=(2 * fp,), row_map=[(0, f, 0), (f, f, fp)])
             pack.add(lin2.weight, op_shape=(lin2.out_features, fp))
         pack.add(lin2.bias)
+        # the transposed FF2 operand [Fp, D] for the fused dgrad + GEGLU-backward GEMM (K-major B operand); 5.6 MB per layer
+        e2 = pack.lookup(lin2.weight)
+        w2t = torch.zeros((e2.op.shape[1], e2.op.shape[0]), device=pack.device, dtype=BF16)
+        pack.post_copies.append((w2t, e2.op.t()))
+        ff.__dict__['_vbx_w2t'] = w2t
         for n in (attn_norm, ff_norm):
             if hasattr(n, 'to_gamma'):
                 norms.append(n)
