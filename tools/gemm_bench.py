@@ -29,7 +29,36 @@ def timeit(fn, iters=10, warm=3):
     return e0.elapsed_time(e1) / iters * 1e3
 
 
+def bench_ff_bwd(T, out):
+    """FF2 dgrad GEMM with the GEGLU-backward epilogue (one launch) against the pair it replaces (cuBLASLt dgrad + vbx_geglu_bwd)."""
+    K, Fp = 1024, 2752
+    from voicebox_pytorch_b200._lib import call, ptr, stream
+    dy = torch.randn(T, K, device='cuda').to(BF16)
+    w2 = (torch.randn(K, Fp, device='cuda') / Fp ** 0.5).to(BF16)          # second Linear's weight [out, in]
+    w2t = w2.t().contiguous()                                              # [Fp, K]: the dgrad GEMM's B operand, K-major
+    h = torch.randn(T, 2 * Fp, device='cuda').to(BF16)
+    dh = torch.empty_like(h)
+    db = torch.zeros(2 * Fp, device='cuda')
+
+    def pair():
+        dg = dy @ w2
+        call('vbx_geglu_bwd', ptr(h), ptr(dg), ptr(dh), ptr(db), T, Fp, stream())
+
+    def fused():
+        call('vbx_ff2_dgrad_geglu_bwd', ptr(dy), ptr(w2t), ptr(h), ptr(dh), ptr(db), T, Fp, K, stream())
+
+    t_gemm = timeit(lambda: dy @ w2)
+    t_pair = timeit(pair)
+    t_fused = timeit(fused)
+    out[f'ff2_dgrad_geglu_bwd_T{T}'] = dict(cublaslt_dgrad_us=t_gemm, pair_us=t_pair, fused_us=t_fused)
+    print(f'ff2 dgrad + geglu bwd T={T:6d}  cuBLASLt dgrad {t_gemm:8.1f} us, + geglu_bwd kernel {t_pair:8.1f} us   fused {t_fused:8.1f} us '
+          f' ratio {t_pair / t_fused:5.2f}', flush=True)
+
+
 out = {}
+if os.environ.get('VBX_GEMM_BENCH') == 'bwd':
+    bench_ff_bwd(64 * 1040, out)
+    sys.exit(0)
 for T in (64 * 1040, 16 * 2064):
     for name, K, N, bias in (('to_qkv', 1024, 3072, False), ('to_out', 1024, 1024, False), ('ff2', 2752, 1024, True)):
         a = torch.randn(T, K, device='cuda').to(BF16)
@@ -55,5 +84,6 @@ for T in (64 * 1040, 16 * 2064):
                                   fused_with_h_tflops=fl / t_h / 1e6, fused_no_h_tflops=fl / t_noh / 1e6)
     print(f'ff1+geglu T={T:6d}  cuBLASLt GEMM {t_gemm:8.1f} us, + geglu kernel {t_lib:8.1f} us   fused (h written) {t_h:8.1f} us '
           f'({fl / t_h / 1e6:7.1f} TF/s)   fused (no h) {t_noh:8.1f} us ({fl / t_noh / 1e6:7.1f} TF/s)', flush=True)
+    bench_ff_bwd(T, out)
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'gemm_bench.json'), 'w'), indent=1)

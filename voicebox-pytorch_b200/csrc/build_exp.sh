@@ -11,9 +11,10 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 DEFS=(${VBX_EXP_DEFS:--DVBX_EXP_TAIL=1})
 OUT="${VBX_EXP_OUT:-libvbx_exp.so}"
 TAG="${OUT%.so}"
+SRC="${VBX_EXP_SRC:-attn}"     # which translation unit gets the experimental defines (attn or gemm)
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v "${DEFS[@]}" \
-  -c "$HERE/attn.cu" -o "$HERE/../build/attn_$TAG.o" 2> "$HERE/../build/attn_$TAG.ptxas.log" || { cat "$HERE/../build/attn_$TAG.ptxas.log"; exit 1; }
+  -c "$HERE/$SRC.cu" -o "$HERE/../build/${SRC}_$TAG.o" 2> "$HERE/../build/${SRC}_$TAG.ptxas.log" || { cat "$HERE/../build/${SRC}_$TAG.ptxas.log"; exit 1; }
 OBJS=()
-for f in api norm_ffn cfm_ode convpos qkrope optim pack gemm; do OBJS+=("$HERE/../build/$f.o"); done
-"$NVCC" -shared -o "$HERE/../lib/$OUT" "${OBJS[@]}" "$HERE/../build/attn_$TAG.o" -lcudart
+for f in api norm_ffn cfm_ode convpos qkrope optim pack gemm attn; do [ "$f" = "$SRC" ] || OBJS+=("$HERE/../build/$f.o"); done
+"$NVCC" -shared -o "$HERE/../lib/$OUT" "${OBJS[@]}" "$HERE/../build/${SRC}_$TAG.o" -lcudart
 echo "built $HERE/../lib/$OUT (${DEFS[*]})"

@@ -47,6 +47,20 @@ VBX_DEVINL void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int 
                : "memory");
 }
 VBX_DEVINL void tma_wait_group_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// single-slice variant of store_block (below): the slice's previous store must have finished reading before it is rewritten
+VBX_DEVINL void store_block_single(uint8_t* slice, const uint32_t (&pk)[32], const CUtensorMap* map, int col, int row, int lane) {
+  if (lane == 0) tma_wait_group_read0();
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<uint4*>(slice + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(map, slice, col, row);
+    tma_commit_group();
+  }
+}
 // one box from global memory into the SAME shared-memory offset of every CTA of the cluster named in cta_mask; each destination
 // CTA's mbarrier (same offset) receives the complete_tx
 VBX_DEVINL void tma_load_2d_multicast(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
@@ -308,52 +322,56 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
 // FF2 data-gradient GEMM with the GEGLU backward as its epilogue (vp.py:337-348, backward):
 //   dg = dy W2            [M, Fp]   (A = dy [M, D] K-major;  B = W2^T operand [Fp, D] K-major, zero rows beyond F)
 //   dh[:, :Fp]  = dg * gelu_erf(gate)              dh[:, Fp:] = dg * value * gelu_erf'(gate)          (h = [value | gate], bf16)
-//   db1[c]     += sum over rows of dh[:, c]        (fp32 atomics; the bias gradient of the first Linear)
+//   db1[c]     += sum over rows of dh[:, c]        (fp32; the bias gradient of the first Linear)
 // Replaces the library dgrad GEMM *and* the stand-alone geglu_bwd pass (1.83 GB of HBM traffic per layer at cfg3: dg is never
-// written, h is read once, dh is written once).  Same main loop as gemm_bf16_kernel, 3 stages (the staging area doubles), EIGHT
-// epilogue warps: the GEGLU backward costs ~2.5x the forward's math per element, four warps could not drain a 128 x 256
-// accumulator within one tile's main loop.  Warps 2-5 take accumulator columns [0,128), warps 6-9 columns [128,256); both sets
-// cover the four TMEM lane quarters.  Column sums: a 5-step butterfly leaves lane l with the sums of columns 2l, 2l+1 of each
-// 64-column chunk (62 shuffles per 64 values), then one atomic per column per warp.
+// written, h is read once, dh is written once).  Same main loop as gemm_bf16_kernel, 3 stages, EIGHT epilogue warps (the GEGLU
+// backward costs ~2.5x the forward's math per element): warps 2-5 take accumulator columns [0,128), warps 6-9 columns [128,256);
+// both sets cover the four TMEM lane quarters.  Per 64-column chunk a warp
+//   1. TMA-loads its [32 rows x 64] value and gate blocks of h into its two 4 KB slices (issued before it waits for the
+//      accumulator, so the first chunk's latency hides behind the main loop).  Measured (tools/trip9.sh): per-thread row loads --
+//      32 different 128-byte lines per warp instruction -- made the first version 1,544 us, 2.4x SLOWER than the pair it
+//      replaces; with the loads stubbed out the same kernel ran in 354 us;
+//   2. computes dh for its row, overwrites the slices in place and TMA-stores them;
+//   3. reads the column sums back from the staged bf16 block (32 conflict-free LDS per lane; a register butterfly over 128 live
+//      floats spilled) and adds them into a shared-memory vector -- the value half lives in cluster rank 0's shared memory, the
+//      gate half in rank 1's (red.shared::cluster), flushed to global once per CTA at the end.  Global atomics per warp per tile
+//      (12 M per launch on 5,504 addresses) cost 240 us.  Without a cluster (single tile row) the sums go to global directly.
 // =====================================================================================================================
+// VBX_BWD_ABL: development-only ablation mask of the backward epilogue (1: no bias-gradient sums, 4: no GELU math, 8: no dh
+// stores) used by tools/gemm_bench.py to attribute its time; the product builds with 0
+#ifndef VBX_BWD_ABL
+#define VBX_BWD_ABL 0
+#endif
 namespace gemmb {
 constexpr int kBM = 128, kBN = 256, kBK = 64, kStages = 3;
 constexpr uint32_t kABytes = kBM * kBK * 2, kBBytes = kBN * kBK * 2, kStageBytes = kABytes + kBBytes;
-constexpr uint32_t kOffOut = kStages * kStageBytes;                 // 4 x [128 rows][64 bf16] staging blocks (2 per column half)
-constexpr uint32_t kOutBlockBytes = kBM * 64 * 2;
-constexpr uint32_t kOffBar = kOffOut + 4 * kOutBlockBytes;
-enum { FULL = 0, EMPTY = kStages, TFULL = 2 * kStages, TEMPTY = 2 * kStages + 2, NUM_BARS = 2 * kStages + 4 };
-constexpr uint32_t kSmemBytes = kOffBar + NUM_BARS * 8 + 16;
-static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB)");
+constexpr uint32_t kOffOut = kStages * kStageBytes;                 // 8 warps x 2 slices x 4 KB: [32 rows][64 bf16] value / gate blocks
+constexpr uint32_t kOffBar = kOffOut + 8 * 8192;
+enum { FULL = 0, EMPTY = kStages, TFULL = 2 * kStages, TEMPTY = 2 * kStages + 2, HFULL = 2 * kStages + 4, NUM_BARS = 2 * kStages + 12 };
+constexpr uint32_t kOffDb = kOffBar + 256;                          // f32 [Fp]: column sums of dh (this rank's half of the bias gradient)
+constexpr uint32_t kMaxSmem = 232448;
 constexpr int kThreads = 320;
 }  // namespace gemmb
 
-// butterfly over the 32 lanes: x[0..N) per lane in -> after the 5 steps lane l holds in x[0], x[1] the sums over all lanes of
-// the original elements 2l and 2l+1  (N = 64)
-VBX_DEVINL void warp_colsum64(float (&x)[64], int lane) {
-#pragma unroll
-  for (int s = 16, n = 64; s >= 1; s >>= 1, n >>= 1) {
-    const bool upper = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (i < n / 2) {
-        const float send = upper ? x[i] : x[i + n / 2];
-        const float keep = upper ? x[i + n / 2] : x[i];
-        x[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-      }
-    }
-  }
+VBX_DEVINL uint32_t mapa_shared(uint32_t addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+  return r;
+}
+VBX_DEVINL void red_add_f32_cluster(uint32_t cluster_addr, float v) {
+  asm volatile("red.relaxed.cluster.shared::cluster.add.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
 }
 
 template <int CLUSTER>
 __global__ void __launch_bounds__(gemmb::kThreads, 1)
 gemm_geglu_bwd_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW, const __grid_constant__ CUtensorMap mO0,
-                      const __grid_constant__ CUtensorMap mO1, const uint16_t* __restrict__ h, float* __restrict__ db, int M, int Fp, int K,
-                      int m_tiles, int n_tiles) {
+                      const __grid_constant__ CUtensorMap mO1, const __grid_constant__ CUtensorMap mH, float* __restrict__ db, int M, int Fp,
+                      int K, int m_tiles, int n_tiles) {
   using namespace gemmb;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + NUM_BARS * 8);
+  float* s_db = reinterpret_cast<float*>(smem + kOffDb);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (K + kBK - 1) / kBK;
   const int rank = CLUSTER == 2 ? (int)cluster_ctarank() : 0;
@@ -364,6 +382,8 @@ gemm_geglu_bwd_kernel(const __grid_constant__ CUtensorMap mA, const __grid_const
   const int m0 = (CLUSTER == 2 ? 2 * ((wi) / n_tiles) + rank : (wi) / n_tiles) * kBM,        \
             j0 = ((wi) % n_tiles) * kBN
 
+  if (CLUSTER == 2)
+    for (int i = threadIdx.x; i < Fp; i += blockDim.x) s_db[i] = 0.f;
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
     for (int s = 0; s < kStages; ++s) {
@@ -374,6 +394,7 @@ gemm_geglu_bwd_kernel(const __grid_constant__ CUtensorMap mA, const __grid_const
       mbar_init(&bars[TFULL + a], 1);
       mbar_init(&bars[TEMPTY + a], 256);
     }
+    for (int w = 0; w < 8; ++w) mbar_init(&bars[HFULL + w], 1);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -381,6 +402,7 @@ gemm_geglu_bwd_kernel(const __grid_constant__ CUtensorMap mA, const __grid_const
     tma_prefetch_desc(&mW);
     tma_prefetch_desc(&mO0);
     tma_prefetch_desc(&mO1);
+    tma_prefetch_desc(&mH);
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
@@ -442,32 +464,40 @@ gemm_geglu_bwd_kernel(const __grid_constant__ CUtensorMap mA, const __grid_const
     const int q = warp & 3;                                   // TMEM lane quarter
     const int grp = (warp - 2) >> 2;                          // 0: accumulator columns [0,128), 1: [128,256)
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint8_t* slice0 = smem + kOffOut + (grp * 2) * kOutBlockBytes + q * 4096;
-    uint8_t* slice1 = slice0 + kOutBlockBytes;
-    int tcount = 0, blk = 0;
+    uint8_t* slice_v = smem + kOffOut + (warp - 2) * 8192;    // value block in, d(value) block out
+    uint8_t* slice_g = slice_v + 4096;                        // gate block in, d(gate) block out
+    uint64_t* hbar = &bars[HFULL + (warp - 2)];
+    // where this warp's column sums go: shared-memory vectors of the cluster pair (value half: rank 0, gate half: rank 1)
+    const uint32_t sdb_v = CLUSTER == 2 ? mapa_shared(smem_u32(s_db), 0) : 0u;
+    const uint32_t sdb_g = CLUSTER == 2 ? mapa_shared(smem_u32(s_db), 1) : 0u;
+    int tcount = 0, hcount = 0;
     for (int wi = w0; wi < nwork; wi += wstep, ++tcount) {
       const int acc = tcount & 1;
       VBX_TILE_COORDS(wi);
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < M;
-      mbar_wait(&bars[TFULL + acc], (tcount >> 1) & 1);
-      tc_fence_after();
+      const int row0 = m0 + q * 32;                           // rows >= M: TMA zero-fills h and dy, so their dh rows are zeros
       const uint32_t t_acc = t_lane + (uint32_t)acc * kBN + grp * 128;
 #pragma unroll 1
       for (int jj = 0; jj < 2; ++jj) {
         const int col = j0 + grp * 128 + jj * 64;             // first dg / value column of this 64-column chunk
         const bool col_ok = col < Fp;                         // Fp % 64 == 0: a chunk is entirely inside or entirely outside
-        float sv[64], sg[64];                                 // bf16-rounded dh values of this row: value half, gate half
         if (col_ok) {
-          const uint16_t* hp = h + (int64_t)(row_ok ? row : 0) * 2 * Fp + col;   // this row's value / gate entries of h
+          if (lane == 0) {
+            tma_wait_group_read0();                           // the previous chunk's stores have finished reading the slices
+            mbar_arrive_expect_tx(hbar, 8192);
+            tma_load_2d(slice_v, &mH, hbar, col, row0);
+            tma_load_2d(slice_g, &mH, hbar, Fp + col, row0);
+          }
+        }
+        if (jj == 0) {
+          mbar_wait(&bars[TFULL + acc], (tcount >> 1) & 1);
+          tc_fence_after();
+        }
+        if (col_ok) {
+          mbar_wait(hbar, hcount & 1);
+          ++hcount;
+          uint32_t pv[32], pg[32];
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
-            uint4 hv[4], hg[4];                                 // 32 value + 32 gate entries: one 64-byte half line each
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              hv[i] = row_ok ? ldg_nc_16(hp + hf * 32 + 8 * i) : make_uint4(0, 0, 0, 0);
-              hg[i] = row_ok ? ldg_nc_16(hp + Fp + hf * 32 + 8 * i) : make_uint4(0, 0, 0, 0);
-            }
             float d[32];
             tmem_ld32(t_acc + jj * 64 + hf * 32, d);
             if (jj == 1 && hf == 1) {                          // last read of this accumulator half by this thread
@@ -476,41 +506,71 @@ gemm_geglu_bwd_kernel(const __grid_constant__ CUtensorMap mA, const __grid_const
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              float v8[8], g8[8];
-              unpack8(hv[i], v8);
-              unpack8(hg[i], g8);
+              const int c = hf * 4 + i;                        // 16-byte chunk of this lane's 128-byte row, at position c ^ (lane & 7)
+              const uint4 hv = *reinterpret_cast<const uint4*>(slice_v + lane * 128 + ((c ^ (lane & 7)) << 4));
+              const uint4 hg = *reinterpret_cast<const uint4*>(slice_g + lane * 128 + ((c ^ (lane & 7)) << 4));
+              float v8[8], g8[8], dv8[8], dg8[8];
+              unpack8(hv, v8);
+              unpack8(hg, g8);
 #pragma unroll
               for (int x = 0; x < 8; ++x) {
-                const int c = hf * 32 + i * 8 + x;
                 // dg is a bf16 tensor in the reference's autocast backward: round it before it is used
                 const float dd = __bfloat162float(__float2bfloat16_rn(d[i * 8 + x]));
+#if VBX_BWD_ABL & 4
+                dv8[x] = dd * g8[x];
+                dg8[x] = dd * v8[x];
+#else
                 float e;
                 const float cdf = normal_cdf(g8[x], e);
-                const float dval = dd * (g8[x] * cdf);
-                const float dgate = dd * v8[x] * fmaf(g8[x] * 0.3989422804014327f, e, cdf);
-                sv[c] = __bfloat162float(__float2bfloat16_rn(dval));
-                sg[c] = __bfloat162float(__float2bfloat16_rn(dgate));
+                dv8[x] = dd * (g8[x] * cdf);
+                dg8[x] = dd * v8[x] * fmaf(g8[x] * 0.3989422804014327f, e, cdf);
+#endif
+              }
+#pragma unroll
+              for (int x = 0; x < 4; ++x) {
+                pv[c * 4 + x] = pack_bf16x2(dv8[2 * x], dv8[2 * x + 1]);
+                pg[c * 4 + x] = pack_bf16x2(dg8[2 * x], dg8[2 * x + 1]);
               }
             }
           }
-          uint32_t pv[32], pg[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            pv[i] = pack_bf16x2(sv[2 * i], sv[2 * i + 1]);
-            pg[i] = pack_bf16x2(sg[2 * i], sg[2 * i + 1]);
+          for (int half = 0; half < 2; ++half) {
+            uint8_t* slice = half ? slice_g : slice_v;
+            // each lane overwrites the row it alone has read
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint32_t* pk = half ? pg : pv;
+              *reinterpret_cast<uint4*>(slice + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+#if !(VBX_BWD_ABL & 8)
+            if (lane == 0) {
+              tma_store_2d(half ? &mO1 : &mO0, slice, col, row0);
+              tma_commit_group();
+            }
+#endif
+#if !(VBX_BWD_ABL & 1)
+            // column sums over this warp's 32 rows: lane l owns columns 2l, 2l+1; row r's 16-byte chunk (l / 4) sits at chunk
+            // position (l / 4) ^ (r & 7) -> the 32 lanes hit 32 distinct banks
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              const uint32_t w = *reinterpret_cast<const uint32_t*>(slice + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+              s0 += __uint_as_float(w << 16);
+              s1 += __uint_as_float(w & 0xffff0000u);
+            }
+            if (CLUSTER == 2) {
+              const uint32_t dst = (half ? sdb_g : sdb_v) + (uint32_t)(col + 2 * lane) * 4u;
+              red_add_f32_cluster(dst, s0);
+              red_add_f32_cluster(dst + 4u, s1);
+            } else {
+              atomicAdd(db + half * Fp + col + 2 * lane, s0);
+              atomicAdd(db + half * Fp + col + 2 * lane + 1, s1);
+            }
+#endif
           }
-          store_block((blk & 1) ? slice1 : slice0, pv, &mO0, col, m0 + q * 32, lane);
-          ++blk;
-          store_block((blk & 1) ? slice1 : slice0, pg, &mO1, col, m0 + q * 32, lane);
-          ++blk;
-          // bias gradient of the first Linear: column sums of dh over this warp's 32 rows (rows >= M contribute zeros: their
-          // dy rows were zero-filled by TMA)
-          warp_colsum64(sv, lane);
-          warp_colsum64(sg, lane);
-          atomicAdd(db + col + 2 * lane, sv[0]);
-          atomicAdd(db + col + 2 * lane + 1, sv[1]);
-          atomicAdd(db + Fp + col + 2 * lane, sg[0]);
-          atomicAdd(db + Fp + col + 2 * lane + 1, sg[1]);
+          __syncwarp();                                        // every lane has read its sums before lane 0 reloads the slices
         } else if (jj == 1) {                                   // (warp-uniform) nothing to do, but the accumulator must be released
           tc_fence_before();
           mbar_arrive(&bars[TEMPTY + acc]);
@@ -521,7 +581,10 @@ gemm_geglu_bwd_kernel(const __grid_constant__ CUtensorMap mA, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (CLUSTER == 2) cluster_sync_all();
+  if (CLUSTER == 2) {
+    cluster_sync_all();                                        // every red of both CTAs has landed
+    for (int i = threadIdx.x; i < Fp; i += blockDim.x) atomicAdd(db + rank * Fp + i, s_db[i]);
+  }
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 #undef VBX_TILE_COORDS
 }
@@ -616,10 +679,11 @@ extern "C" int vbx_ff2_dgrad_geglu_bwd(const uint16_t* dy, const uint16_t* w2t, 
   VBX_REQUIRE(M > 0 && Fp >= 64 && K > 0 && M < (1ll << 31) && Fp < (1ll << 30) && K < (1ll << 31) && Fp % 64 == 0 && K % 8 == 0,
               VBX_E_SHAPE);
   VBX_REQUIRE(VBX_ALIGNED16(dy) && VBX_ALIGNED16(w2t) && VBX_ALIGNED16(h) && VBX_ALIGNED16(dh), VBX_E_ALIGN);
-  CUtensorMap mA, mW, mO0, mO1;
+  CUtensorMap mA, mW, mO0, mO1, mH;
   int rc;
   if ((rc = make_tmap_bf16_2d(&mA, dy, K, M, K, kBM)) != VBX_OK) return rc;
   if ((rc = make_tmap_bf16_2d(&mW, w2t, K, Fp, K, 128)) != VBX_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&mH, h, 2 * Fp, M, 2 * Fp, 32)) != VBX_OK) return rc;
   if ((rc = make_tmap_bf16_2d(&mO0, dh, Fp, M, 2 * Fp, 32)) != VBX_OK) return rc;
   if ((rc = make_tmap_bf16_2d(&mO1, dh + Fp, Fp, M, 2 * Fp, 32)) != VBX_OK) return rc;
   const int m_tiles = (int)((M + kBM - 1) / kBM), n_tiles = (int)((Fp + kBN - 1) / kBN);
@@ -635,7 +699,9 @@ extern "C" int vbx_ff2_dgrad_geglu_bwd(const uint16_t* dy, const uint16_t* w2t, 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = kSmemBytes;
+  const uint32_t smem_bytes = kOffDb + (uint32_t)(cluster2 ? Fp * 4 : 0);
+  if (smem_bytes > kMaxSmem) return VBX_E_UNSUPPORTED;   // the per-CTA half of the bias-gradient vector must fit (Fp <= 4800)
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -645,10 +711,10 @@ extern "C" int vbx_ff2_dgrad_geglu_bwd(const uint16_t* dy, const uint16_t* w2t, 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   auto kern = cluster2 ? gemm_geglu_bwd_kernel<2> : gemm_geglu_bwd_kernel<1>;
-  cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (ce != cudaSuccess) return (int)ce;
   const int iM = (int)M, iF = (int)Fp, iK = (int)K;
-  ce = cudaLaunchKernelEx(&cfg, kern, mA, mW, mO0, mO1, h, db1, iM, iF, iK, m_tiles, n_tiles);
+  ce = cudaLaunchKernelEx(&cfg, kern, mA, mW, mO0, mO1, mH, db1, iM, iF, iK, m_tiles, n_tiles);
   if (ce != cudaSuccess) return (int)ce;
   return VBX_LAUNCH_RC();
 }
