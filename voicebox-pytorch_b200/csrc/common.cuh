@@ -97,6 +97,32 @@ VBX_DEVINL void st8f(float* p, const float f[8]) {
   }
 }
 
+// 4-element (8 / 16 byte) accesses
+VBX_DEVINL uint2 ldg_nc_8(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+VBX_DEVINL void stg_8(void* p, uint2 v) {
+  asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y));
+}
+VBX_DEVINL void ld4f(const float* p, float* f, bool rw) {   // rw: the buffer may be written by this kernel (no .nc)
+  const uint4 a = rw ? ldg_16(p) : ldg_nc_16(p);
+  f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
+}
+VBX_DEVINL void st4f(float* p, const float* f) {
+  stg_16(p, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+}
+VBX_DEVINL void ld4h(const uint16_t* p, float* f) {
+  const uint2 u = ldg_nc_8(p);
+  const float2 a = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), b = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+VBX_DEVINL void st4h(uint16_t* p, const float* f) {
+  __nv_bfloat162 a = f2bf(f[0], f[1]), b = f2bf(f[2], f[3]);
+  stg_8(p, make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b)));
+}
+
 VBX_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -116,6 +142,17 @@ VBX_DEVINL float ex2_approx(float x) {  // MUFU.EX2, rel err 2^-22; exp2f() adds
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// L2 prefetch of a contiguous, 16-byte aligned range (one instruction, no registers held): the row kernels are latency bound
+// at 14-32 resident warps per SM (ncu: every stall is long-scoreboard, DRAM at 3.3-4.7 TB/s), so each warp announces the NEXT
+// row it will touch while it works on the current one and its demand loads then hit L2.  VBX_ROW_PREFETCH=0 compiles it out.
+#ifndef VBX_ROW_PREFETCH
+#define VBX_ROW_PREFETCH 1
+#endif
+VBX_DEVINL void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+#if VBX_ROW_PREFETCH
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#endif
 }
 VBX_DEVINL float normal_cdf(float x, float& e) {
   const float z = fabsf(x) * 0.70710678118654752f;

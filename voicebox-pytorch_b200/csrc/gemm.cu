@@ -342,6 +342,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
 #ifndef VBX_BWD_ABL
 #define VBX_BWD_ABL 0
 #endif
+#ifndef VBX_BWD_F32X2
+#define VBX_BWD_F32X2 1
+#endif
 namespace gemmb {
 constexpr int kBM = 128, kBN = 256, kBK = 64, kStages = 3;
 constexpr uint32_t kABytes = kBM * kBK * 2, kBBytes = kBN * kBK * 2, kStageBytes = kABytes + kBBytes;
@@ -512,6 +515,36 @@ gemm_geglu_bwd_kernel(const __grid_constant__ CUtensorMap mA, const __grid_const
               float v8[8], g8[8], dv8[8], dg8[8];
               unpack8(hv, v8);
               unpack8(hg, g8);
+#if VBX_BWD_F32X2
+              // two elements per instruction on the packed-fp32 pipe (FFMA2 / FMUL2): the epilogue is instruction-issue bound
+              // (~26 scalar instructions per element x 32 K elements per tile against a 13.7 k-clock main loop); same
+              // formula and operation order as normal_cdf() in common.cuh, so the results are bit-identical
+#pragma unroll
+              for (int x = 0; x < 8; x += 2) {
+                const float2 g2 = make_float2(g8[x], g8[x + 1]), v2 = make_float2(v8[x], v8[x + 1]);
+                // dg is a bf16 tensor in the reference's autocast backward: round it before it is used
+                const float2 dd2 = make_float2(__bfloat162float(__float2bfloat16_rn(d[i * 8 + x])),
+                                               __bfloat162float(__float2bfloat16_rn(d[i * 8 + x + 1])));
+                const float2 z2 = __fmul2_rn(make_float2(fabsf(g2.x), fabsf(g2.y)), make_float2(0.70710678118654752f, 0.70710678118654752f));
+                const float2 den = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), z2, make_float2(1.f, 1.f));
+                const float2 t2 = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+                const float2 a2 = __fmul2_rn(__fmul2_rn(make_float2(-1.4426950408889634f, -1.4426950408889634f), z2), z2);
+                const float2 e2 = make_float2(ex2_approx(a2.x), ex2_approx(a2.y));
+                float2 p2 = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t2, make_float2(-1.453152027f, -1.453152027f));
+                p2 = __ffma2_rn(p2, t2, make_float2(1.421413741f, 1.421413741f));
+                p2 = __ffma2_rn(p2, t2, make_float2(-0.284496736f, -0.284496736f));
+                p2 = __ffma2_rn(p2, t2, make_float2(0.254829592f, 0.254829592f));
+                const float2 he = __fmul2_rn(__fmul2_rn(__fmul2_rn(make_float2(0.5f, 0.5f), p2), t2), e2);     // 0.5 erfc(z)
+                const float2 cdf = make_float2(g2.x >= 0.f ? 1.0f - he.x : he.x, g2.y >= 0.f ? 1.0f - he.y : he.y);
+                const float2 dv2 = __fmul2_rn(dd2, __fmul2_rn(g2, cdf));
+                const float2 in2 = __ffma2_rn(__fmul2_rn(g2, make_float2(0.3989422804014327f, 0.3989422804014327f)), e2, cdf);
+                const float2 dg2 = __fmul2_rn(__fmul2_rn(dd2, v2), in2);
+                dv8[x] = dv2.x;
+                dv8[x + 1] = dv2.y;
+                dg8[x] = dg2.x;
+                dg8[x + 1] = dg2.y;
+              }
+#else
 #pragma unroll
               for (int x = 0; x < 8; ++x) {
                 // dg is a bf16 tensor in the reference's autocast backward: round it before it is used
@@ -526,6 +559,7 @@ gemm_geglu_bwd_kernel(const __grid_constant__ CUtensorMap mA, const __grid_const
                 dg8[x] = dd * v8[x] * fmaf(g8[x] * 0.3989422804014327f, e, cdf);
 #endif
               }
+#endif
 #pragma unroll
               for (int x = 0; x < 4; ++x) {
                 pv[c * 4 + x] = pack_bf16x2(dv8[2 * x], dv8[2 * x + 1]);

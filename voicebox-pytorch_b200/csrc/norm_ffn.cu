@@ -10,31 +10,6 @@ namespace vbx {
 // accesses each touched half of 32 different 32-byte sectors, doubling the L2 <-> SM sector traffic of x / dx (0.71-0.75 of
 // the HBM roofline in round 1 although DRAM bytes matched the algorithmic count).
 VBX_DEVINL int grp(int c, int hf, int lane) { return c * 256 + hf * 128 + lane * 4; }
-VBX_DEVINL uint2 ldg_nc_8(const void* p) {
-  uint2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-  return r;
-}
-VBX_DEVINL void stg_8(void* p, uint2 v) {
-  asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y));
-}
-VBX_DEVINL void ld4f(const float* p, float* f, bool rw) {   // rw: the buffer may be written by this kernel (no .nc)
-  const uint4 a = rw ? ldg_16(p) : ldg_nc_16(p);
-  f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
-}
-VBX_DEVINL void st4f(float* p, const float* f) {
-  stg_16(p, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
-}
-VBX_DEVINL void ld4h(const uint16_t* p, float* f) {
-  const uint2 u = ldg_nc_8(p);
-  const float2 a = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), b = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
-}
-VBX_DEVINL void st4h(uint16_t* p, const float* f) {
-  __nv_bfloat162 a = f2bf(f[0], f[1]), b = f2bf(f[2], f[3]);
-  stg_8(p, make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b)));
-}
-
 // ------------------------------------------------------------------------------------------------------------------
 // residual add + (adaptive) RMSNorm, forward.   One warp per token row; element ownership: grp() above.
 // ------------------------------------------------------------------------------------------------------------------
@@ -55,6 +30,15 @@ __global__ void __launch_bounds__(256, (C <= 4) ? 4 : 2) adarms_fwd_kernel(const
     float v[C][8];
     float ss = 0.f;
     const uint16_t* bri = branch != nullptr ? branch + b * xbs + (row0 + r) * D : nullptr;
+    {
+      // the block that will take this SM slot next is ~one residency wave (4 blocks x 148 SMs x 8 rows) ahead: announce its row
+      const int64_t ahead = row + (int64_t)kNumSM * 4 * 8;
+      if (lane == 0 && ahead < B * rows && (D & 7) == 0) {
+        const int64_t b2 = ahead / rows, r2 = ahead - b2 * rows;
+        prefetch_l2_bulk(x_in + b2 * xbs + (row0 + r2) * D, (uint32_t)D * 4u);
+        if (branch != nullptr) prefetch_l2_bulk(branch + b2 * xbs + (row0 + r2) * D, (uint32_t)D * 2u);
+      }
+    }
 #pragma unroll
     for (int c = 0; c < C; ++c) {
 #pragma unroll
@@ -148,6 +132,14 @@ __global__ void __launch_bounds__(256, 2) adarms_bwd_kernel(const float* __restr
   for (int64_t r = r_begin + warp; r < r_end; r += (blockDim.x >> 5)) {
     const int64_t row = b * rows + r;
     const float* xi = x + b * xbs + (row0 + r) * D;
+    if (lane == 0 && (D & 7) == 0) {   // this warp's next row; and the residual-stream gradient this row needs after the reduction
+      if (dx_res != nullptr) prefetch_l2_bulk(dx_res + row * D, (uint32_t)D * 4u);
+      const int64_t rn = r + (blockDim.x >> 5);
+      if (rn < r_end) {
+        prefetch_l2_bulk(xi + (int64_t)(blockDim.x >> 5) * D, (uint32_t)D * 4u);
+        prefetch_l2_bulk(dh + (row + (blockDim.x >> 5)) * D, (uint32_t)D * 2u);
+      }
+    }
     const float rinv = rstd[row];
     const float s1 = sqrt_d * rinv;  // d h / d x leading factor
     float xv[C][8], gv[C][8];

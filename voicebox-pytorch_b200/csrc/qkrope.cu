@@ -37,149 +37,277 @@ VBX_DEVINL void ld8c(const float* p, float f[8]) {  // small tables (cos/sin/gam
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = c.x; f[5] = c.y; f[6] = c.z; f[7] = c.w;
 }
 
-__global__ void __launch_bounds__(256) qkrope_fwd_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ cosv,
+// Token order.  The q/k blocks of qkv are token-major, q_h / k_h / dq_h / dk_h head-major ([b, h, n, 64]): whichever way a
+// block walks, one side is made of 128-256 byte pieces.  GROUPED order (used whenever the block's vector slots divide into whole
+// tokens, i.e. VPB % 2H == 0): a block takes kTokGroup CONSECUTIVE tokens x all (which, head) pairs per outer step, so within a
+// few microseconds it touches kTokGroup x 4 KB contiguous token-major bytes and, per head, kTokGroup consecutive 128-256 byte
+// pieces = 1-2 KB contiguous head-major bytes (DRAM page and L2 write-combining locality; the strided order reached only
+// 3.3-3.4 TB/s in the backward with every stall a DRAM wait, whatever the occupancy).  Otherwise the round-1 order: a thread
+// group keeps (which, head) and jumps tok_step = grid * VPB / 2H tokens per iteration (grid rounded so that 2H | grid * VPB).
+constexpr int kTokGroup = 8;
+struct TokWalk {
+  int which, h;          // fixed per thread
+  int64_t tok0;          // legacy: first token; grouped: token offset inside a group
+  int64_t step;          // tokens per inner iteration
+  int passes;            // grouped: inner iterations per group
+  int group;             // grouped: tokens per group (>= kTokGroup)
+};
+VBX_DEVINL TokWalk make_walk(int vslot, int vpb, int H, bool grouped) {
+  TokWalk w;
+  if (grouped) {
+    const int pair = vslot % (2 * H);
+    w.which = pair / H;
+    w.h = pair - w.which * H;
+    w.tok0 = vslot / (2 * H);
+    w.step = vpb / (2 * H);
+    w.group = w.step > kTokGroup ? (int)w.step : kTokGroup;
+    w.passes = w.group / (int)w.step;
+  } else {
+    const int64_t vid0 = (int64_t)blockIdx.x * vpb + vslot;
+    const int pair = (int)(vid0 % (2 * H));
+    w.which = pair / H;
+    w.h = pair - w.which * H;
+    w.tok0 = vid0 / (2 * H);
+    w.step = (int64_t)gridDim.x * vpb / (2 * H);
+    w.group = 0;
+    w.passes = 0x7fffffff;
+  }
+  return w;
+}
+
+// U vectors per thread in flight (see the backward below: bytes outstanding per SM, not occupancy, set these kernels' speed)
+#ifndef VBX_QKROPE_FWD_U
+#define VBX_QKROPE_FWD_U 4
+#endif
+#ifndef VBX_QKROPE_FWD_MINB
+#define VBX_QKROPE_FWD_MINB 2
+#endif
+template <int U>
+__global__ void __launch_bounds__(256, VBX_QKROPE_FWD_MINB) qkrope_fwd_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ cosv,
                                                           const float* __restrict__ sinv, const float* __restrict__ gq,
                                                           const float* __restrict__ gk, uint16_t* __restrict__ qh,
-                                                          uint16_t* __restrict__ kh, int64_t B, int64_t N, int H) {
+                                                          uint16_t* __restrict__ kh, int64_t B, int64_t N, int H, int grouped) {
   const int sub = threadIdx.x & (kLpv - 1);
-  const int64_t nvec = B * N * 2 * H;
-  const int64_t stride = (int64_t)gridDim.x * kVecPerBlock;  // a multiple of 2H (host): (which, head) fixed per thread
-  const int64_t vid0 = (int64_t)blockIdx.x * kVecPerBlock + (threadIdx.x / kLpv);
-  VecId id = decode(vid0 < nvec ? vid0 : 0, H);
-  const int64_t tok_step = stride / (2 * H);
-  int64_t b = id.tok / N, n = id.tok - b * N;
-  const float* gam = id.which ? gk : gq;
+  const int64_t total = B * N;
+  const TokWalk w = make_walk(threadIdx.x / kLpv, kVecPerBlock, H, grouped != 0);
+  const float* gam = w.which ? gk : gq;
   float glo[8], ghi[8];
   if (gam != nullptr) {
-    ld8c(gam + id.h * kDh + sub * 8, glo);
-    ld8c(gam + id.h * kDh + 32 + sub * 8, ghi);
+    ld8c(gam + w.h * kDh + sub * 8, glo);
+    ld8c(gam + w.h * kDh + 32 + sub * 8, ghi);
   }
-  for (int64_t vid = vid0;; vid += stride) {
-    const bool active = vid < nvec;  // keep all lanes in the shuffles
-    if (!active) { id.tok = 0; b = 0; n = 0; }
-    const uint16_t* src = qkv + id.tok * (3 * H * kDh) + id.which * (H * kDh) + id.h * kDh + sub * 8;
-    float lo[8], hi[8], cs[8], sn[8];
-    unpack8(ldg_nc_16(src), lo);
-    unpack8(ldg_nc_16(src + 32), hi);
-    ld8c(cosv + n * 32 + sub * 8, cs);
-    ld8c(sinv + n * 32 + sub * 8, sn);
-    if (gam != nullptr) {
-      float ss = 0.f;
+  for (int64_t g = blockIdx.x;; g += gridDim.x) {
+    int64_t tok = grouped ? g * w.group + w.tok0 : w.tok0;
+    if (grouped && g * w.group >= total) break;
+    int64_t b = tok / N, n = tok - b * N;
+    for (int ps = 0; ps < w.passes; ps += U) {
+      uint4 xl[U], xh[U];
+      const int64_t tok_c = tok, b_c = b, n_c = n;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) ss = fmaf(lo[i], lo[i], fmaf(hi[i], hi[i], ss));
-      ss = sum4(ss);
-      const float sc = 8.0f * fminf(rsqrtf(ss), 1e12f);  // F.normalize (x / max(||x||, 1e-12)) * sqrt(64); MUFU.RSQ, rel err 2^-22
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        lo[i] *= sc * glo[i];
-        hi[i] *= sc * ghi[i];
+      for (int u = 0; u < U; ++u) {
+        const int64_t t_ = tok < total ? tok : 0;   // inactive lanes read token 0 and stay in the shuffles
+        const uint16_t* src = qkv + t_ * (3 * H * kDh) + w.which * (H * kDh) + w.h * kDh + sub * 8;
+        xl[u] = ldg_nc_16(src);
+        xh[u] = ldg_nc_16(src + 32);
+        tok += w.step;
+        n += w.step;
+        while (n >= N) { n -= N; ++b; }
       }
-    }
-    float olo[8], ohi[8];
+      int64_t tok2 = tok_c, b2 = b_c, n2 = n_c;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {  // rotate_half([a,b]) = [-b, a]
-      olo[i] = fmaf(lo[i], cs[i], -hi[i] * sn[i]);
-      ohi[i] = fmaf(hi[i], cs[i], lo[i] * sn[i]);
+      for (int u = 0; u < U; ++u) {
+        const bool active = tok2 < total;
+        const int64_t b_ = active ? b2 : 0, n_ = active ? n2 : 0;
+        tok2 += w.step;
+        n2 += w.step;
+        while (n2 >= N) { n2 -= N; ++b2; }
+        float lo[8], hi[8], cs[8], sn[8];
+        unpack8(xl[u], lo);
+        unpack8(xh[u], hi);
+        ld8c(cosv + n_ * 32 + sub * 8, cs);
+        ld8c(sinv + n_ * 32 + sub * 8, sn);
+        if (gam != nullptr) {
+          float ss = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ss = fmaf(lo[i], lo[i], fmaf(hi[i], hi[i], ss));
+          ss = sum4(ss);
+          const float sc = 8.0f * fminf(rsqrtf(ss), 1e12f);  // F.normalize (x / max(||x||, 1e-12)) * sqrt(64); MUFU.RSQ, rel err 2^-22
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            lo[i] *= sc * glo[i];
+            hi[i] *= sc * ghi[i];
+          }
+        }
+        float olo[8], ohi[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {  // rotate_half([a,b]) = [-b, a]
+          olo[i] = fmaf(lo[i], cs[i], -hi[i] * sn[i]);
+          ohi[i] = fmaf(hi[i], cs[i], lo[i] * sn[i]);
+        }
+        if (active) {
+          uint16_t* dst = (w.which ? kh : qh) + ((b_ * H + w.h) * N + n_) * kDh + sub * 8;
+          stg_16(dst, pack8(olo));
+          stg_16(dst + 32, pack8(ohi));
+        }
+      }
+      if (!grouped && __all_sync(0xffffffffu, tok >= total)) break;
     }
-    if (active) {
-      uint16_t* dst = (id.which ? kh : qh) + ((b * H + id.h) * N + n) * kDh + sub * 8;
-      stg_16(dst, pack8(olo));
-      stg_16(dst + 32, pack8(ohi));
-    }
-    if (__all_sync(0xffffffffu, vid + stride >= nvec)) break;
-    id.tok += tok_step;  // advance (b, n) without dividing
-    n += tok_step;
-    while (n >= N) { n -= N; ++b; }
+    if (!grouped) break;
   }
 }
 
 // backward: dy (f32 for q, bf16 for k) -> d qkv[q|k blocks] (bf16), dgamma_q / dgamma_k accumulated in registers (each thread
 // keeps the same (which, head, slice) for its whole loop) and flushed with one atomic per element per thread.
-__global__ void __launch_bounds__(256) qkrope_bwd_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ cosv,
-                                                          const float* __restrict__ sinv, const float* __restrict__ gq,
-                                                          const float* __restrict__ gk, const float* __restrict__ dqh,
-                                                          const uint16_t* __restrict__ dkh, uint16_t* __restrict__ dqkv,
-                                                          float* __restrict__ dgq, float* __restrict__ dgk, int64_t B,
-                                                          int64_t N, int H) {
-  const int sub = threadIdx.x & (kLpv - 1);
-  const int64_t nvec = B * N * 2 * H;
-  const int64_t stride = (int64_t)gridDim.x * kVecPerBlock;
-  const int64_t vid0 = (int64_t)blockIdx.x * kVecPerBlock + (threadIdx.x / kLpv);
-  const VecId id0 = decode(vid0 < nvec ? vid0 : 0, H);
-  const float* gam = id0.which ? gk : gq;
-  float glo[8], ghi[8], dglo[8], dghi[8];
+// EIGHT lanes per head vector here (lane s: elements [4s, 4s+4) and [32+4s, 32+4s+4)): with four lanes the kernel needed 123
+// registers (2 blocks = 14 resident warps per SM) and ~300 dependent instructions per vector per thread.
+constexpr int kLpvB = 8;                      // lanes per vector, backward
+constexpr int kVecPerBlockB = 256 / kLpvB;    // 32
+VBX_DEVINL float sum8(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+VBX_DEVINL void ld4c(const float* p, float f[4]) {  // small tables (cos/sin/gamma): cached loads
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+}
+
+// U tokens per thread are in flight at once: the loads of all U vectors are issued (into packed registers) before the first is
+// processed.  Measured: at one vector per thread the backward sat at 3.3 TB/s whatever the occupancy (14 or 32 warps), the token
+// order or an L2 prefetch -- a warp-iteration only has 384 bytes outstanding, ~12 KB per SM, a quarter of what 7 TB/s x ~1 us
+// needs.
+#ifndef VBX_QKROPE_BWD_U
+#define VBX_QKROPE_BWD_U 4
+#endif
+#ifndef VBX_QKROPE_BWD_MINB
+#define VBX_QKROPE_BWD_MINB 2
+#endif
+template <int U>
+__global__ void __launch_bounds__(256, VBX_QKROPE_BWD_MINB) qkrope_bwd_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ cosv,
+                                                             const float* __restrict__ sinv, const float* __restrict__ gq,
+                                                             const float* __restrict__ gk, const float* __restrict__ dqh,
+                                                             const uint16_t* __restrict__ dkh, uint16_t* __restrict__ dqkv,
+                                                             float* __restrict__ dgq, float* __restrict__ dgk, int64_t B,
+                                                             int64_t N, int H, int grouped) {
+  const int sub = threadIdx.x & (kLpvB - 1);
+  const int64_t total = B * N;
+  const TokWalk w = make_walk(threadIdx.x / kLpvB, kVecPerBlockB, H, grouped != 0);
+  const float* gam = w.which ? gk : gq;
+  float glo[4], ghi[4], dglo[4], dghi[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) glo[i] = ghi[i] = 1.f, dglo[i] = dghi[i] = 0.f;
+  for (int i = 0; i < 4; ++i) glo[i] = ghi[i] = 1.f, dglo[i] = dghi[i] = 0.f;
   if (gam != nullptr) {
-    ld8c(gam + id0.h * kDh + sub * 8, glo);
-    ld8c(gam + id0.h * kDh + 32 + sub * 8, ghi);
+    ld4c(gam + w.h * kDh + sub * 4, glo);
+    ld4c(gam + w.h * kDh + 32 + sub * 4, ghi);
   }
-  VecId id = id0;
-  const int64_t tok_step = stride / (2 * H);
-  int64_t b = id.tok / N, n = id.tok - b * N;
-  for (int64_t vid = vid0;; vid += stride) {
-    const bool active = vid < nvec;
-    if (!active) { id.tok = 0; b = 0; n = 0; }
-    const int64_t hoff = ((b * H + id.h) * N + n) * kDh + sub * 8;
-    float dlo[8], dhi[8], xlo[8], xhi[8], cs[8], sn[8];
-    if (id.which) {
-      unpack8(ldg_nc_16(dkh + hoff), dlo);
-      unpack8(ldg_nc_16(dkh + hoff + 32), dhi);
-    } else {
-      ld8f(dqh + hoff, dlo);
-      ld8f(dqh + hoff + 32, dhi);
-    }
-    const int64_t goff = id.tok * (3 * H * kDh) + id.which * (H * kDh) + id.h * kDh + sub * 8;
-    unpack8(ldg_nc_16(qkv + goff), xlo);
-    unpack8(ldg_nc_16(qkv + goff + 32), xhi);
-    ld8c(cosv + n * 32 + sub * 8, cs);
-    ld8c(sinv + n * 32 + sub * 8, sn);
-    // undo the rotation (transpose): dz_lo = dy_lo c + dy_hi s ; dz_hi = dy_hi c - dy_lo s
-    float zlo[8], zhi[8];
+  bool any = false;
+  for (int64_t g = blockIdx.x;; g += gridDim.x) {
+    int64_t tok = grouped ? g * w.group + w.tok0 : w.tok0;
+    if (grouped && g * w.group >= total) break;
+    int64_t b = tok / N, n = tok - b * N;
+    for (int ps = 0; ps < w.passes; ps += U) {
+      uint4 d0[U], d1[U];          // dy: f32 x 4 (q) or bf16 x 4 in .x/.y (k)
+      uint2 x0[U], x1[U];          // pre-norm q / k, bf16 x 4
+      const int64_t tok_c = tok;   // the compute phase walks (tok, n) again instead of keeping U offsets in registers
+      const int64_t n_c = n;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      zlo[i] = fmaf(dlo[i], cs[i], dhi[i] * sn[i]);
-      zhi[i] = fmaf(dhi[i], cs[i], -dlo[i] * sn[i]);
-    }
-    if (gam != nullptr) {
-      float ss = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) ss = fmaf(xlo[i], xlo[i], fmaf(xhi[i], xhi[i], ss));
-      ss = sum4(ss);
-      const float rinv = fminf(rsqrtf(ss), 1e12f);
-      const float s1 = 8.0f * rinv;
-      float dot = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (active) {
-          dglo[i] = fmaf(zlo[i] * xlo[i], s1, dglo[i]);  // dgamma += dz * xhat * 8
-          dghi[i] = fmaf(zhi[i] * xhi[i], s1, dghi[i]);
+      for (int u = 0; u < U; ++u) {
+        const bool act = tok < total;
+        any |= act;
+        const int64_t t_ = act ? tok : 0, b_ = act ? b : 0, n_ = act ? n : 0;
+        const int64_t hoff = ((b_ * H + w.h) * N + n_) * kDh + sub * 4;
+        const int64_t goff = t_ * (3 * H * kDh) + w.which * (H * kDh) + w.h * kDh + sub * 4;
+        if (w.which) {
+          const uint2 a = ldg_nc_8(dkh + hoff), c = ldg_nc_8(dkh + hoff + 32);
+          d0[u] = make_uint4(a.x, a.y, 0u, 0u);
+          d1[u] = make_uint4(c.x, c.y, 0u, 0u);
+        } else {
+          d0[u] = ldg_nc_16(dqh + hoff);
+          d1[u] = ldg_nc_16(dqh + hoff + 32);
         }
-        zlo[i] *= glo[i];
-        zhi[i] *= ghi[i];
-        dot = fmaf(zlo[i], xlo[i], fmaf(zhi[i], xhi[i], dot));
+        x0[u] = ldg_nc_8(qkv + goff);
+        x1[u] = ldg_nc_8(qkv + goff + 32);
+        tok += w.step;
+        n += w.step;
+        while (n >= N) { n -= N; ++b; }
       }
-      dot = sum4(dot);
-      const float s2 = s1 * rinv * rinv * dot;
+      int64_t tok2 = tok_c, n2 = n_c;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        zlo[i] = fmaf(zlo[i], s1, -xlo[i] * s2);
-        zhi[i] = fmaf(zhi[i], s1, -xhi[i] * s2);
+      for (int u = 0; u < U; ++u) {
+        const bool act = tok2 < total;
+        const int64_t goff = (act ? tok2 : 0) * (3 * H * kDh) + w.which * (H * kDh) + w.h * kDh + sub * 4;
+        const int nn = act ? (int)n2 : 0;
+        tok2 += w.step;
+        n2 += w.step;
+        while (n2 >= N) n2 -= N;
+        // compiler barrier: keeps the (L1-resident) cos / sin loads of later vectors from being hoisted above this one's math --
+        // 32 more live registers, which at 3 blocks per SM spilled 370 bytes and cost more than the unroll gained
+        asm volatile("" ::: "memory");
+        float dlo[4], dhi[4], xlo[4], xhi[4], cs[4], sn[4];
+        if (w.which) {
+          const float2 a = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&d0[u].x)), c = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&d0[u].y));
+          const float2 e = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&d1[u].x)), f = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&d1[u].y));
+          dlo[0] = a.x; dlo[1] = a.y; dlo[2] = c.x; dlo[3] = c.y;
+          dhi[0] = e.x; dhi[1] = e.y; dhi[2] = f.x; dhi[3] = f.y;
+        } else {
+          dlo[0] = __uint_as_float(d0[u].x); dlo[1] = __uint_as_float(d0[u].y); dlo[2] = __uint_as_float(d0[u].z); dlo[3] = __uint_as_float(d0[u].w);
+          dhi[0] = __uint_as_float(d1[u].x); dhi[1] = __uint_as_float(d1[u].y); dhi[2] = __uint_as_float(d1[u].z); dhi[3] = __uint_as_float(d1[u].w);
+        }
+        {
+          const float2 a = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&x0[u].x)), c = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&x0[u].y));
+          const float2 e = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&x1[u].x)), f = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&x1[u].y));
+          xlo[0] = a.x; xlo[1] = a.y; xlo[2] = c.x; xlo[3] = c.y;
+          xhi[0] = e.x; xhi[1] = e.y; xhi[2] = f.x; xhi[3] = f.y;
+        }
+        ld4c(cosv + nn * 32 + sub * 4, cs);
+        ld4c(sinv + nn * 32 + sub * 4, sn);
+        // undo the rotation (transpose): dz_lo = dy_lo c + dy_hi s ; dz_hi = dy_hi c - dy_lo s
+        float zlo[4], zhi[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          zlo[i] = fmaf(dlo[i], cs[i], dhi[i] * sn[i]);
+          zhi[i] = fmaf(dhi[i], cs[i], -dlo[i] * sn[i]);
+        }
+        if (gam != nullptr) {
+          float ss = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ss = fmaf(xlo[i], xlo[i], fmaf(xhi[i], xhi[i], ss));
+          ss = sum8(ss);
+          const float rinv = fminf(rsqrtf(ss), 1e12f);
+          const float s1 = 8.0f * rinv;
+          float dot = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (act) {
+              dglo[i] = fmaf(zlo[i] * xlo[i], s1, dglo[i]);  // dgamma += dz * xhat * 8
+              dghi[i] = fmaf(zhi[i] * xhi[i], s1, dghi[i]);
+            }
+            zlo[i] *= glo[i];
+            zhi[i] *= ghi[i];
+            dot = fmaf(zlo[i], xlo[i], fmaf(zhi[i], xhi[i], dot));
+          }
+          dot = sum8(dot);
+          const float s2 = s1 * rinv * rinv * dot;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            zlo[i] = fmaf(zlo[i], s1, -xlo[i] * s2);
+            zhi[i] = fmaf(zhi[i], s1, -xhi[i] * s2);
+          }
+        }
+        if (act) {
+          st4h(dqkv + goff, zlo);
+          st4h(dqkv + goff + 32, zhi);
+        }
       }
+      if (!grouped && __all_sync(0xffffffffu, tok >= total)) break;
     }
-    if (active) {
-      stg_16(dqkv + goff, pack8(zlo));
-      stg_16(dqkv + goff + 32, pack8(zhi));
-    }
-    if (__all_sync(0xffffffffu, vid + stride >= nvec)) break;
-    id.tok += tok_step;
-    n += tok_step;
-    while (n >= N) { n -= N; ++b; }
+    if (!grouped) break;
   }
-  if (gam != nullptr && vid0 < nvec) {
-    float* dg = (id0.which ? dgk : dgq) + id0.h * kDh + sub * 8;
+  if (gam != nullptr && any) {
+    float* dg = (w.which ? dgk : dgq) + w.h * kDh + sub * 4;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 4; ++i) {
       atomicAdd(dg + i, dglo[i]);
       atomicAdd(dg + 32 + i, dghi[i]);
     }
@@ -190,13 +318,33 @@ __global__ void __launch_bounds__(256) qkrope_bwd_kernel(const uint16_t* __restr
 
 using namespace vbx;
 
-// grid stride (grid*64 vectors) must be a multiple of 2H: round the grid to a multiple of m = 2H / gcd(64, 2H)
-static int64_t rope_grid(int64_t nvec, int64_t H, int blocks_per_sm) {
-  int64_t a = kVecPerBlock, c = 2 * H;
+// grid stride (grid * vectors per block) must be a multiple of 2H: round the grid to a multiple of m = 2H / gcd(vpb, 2H)
+static int64_t rope_grid(int64_t nvec, int64_t H, int blocks_per_sm, int vec_per_block = kVecPerBlock) {
+  int64_t a = vec_per_block, c = 2 * H;
   while (c) { int64_t t = a % c; a = c; c = t; }
   const int64_t m = (2 * H) / a;
-  int64_t grid = grid_for(nvec, kVecPerBlock, blocks_per_sm);
+  int64_t grid = grid_for(nvec, vec_per_block, blocks_per_sm);
   return ((grid + m - 1) / m) * m;
+}
+
+// grouped token order when a block's vector slots divide into whole tokens (see TokWalk); VBX_QKROPE_ORDER=strided forces the
+// round-1 order (A/B runs)
+struct RopeLaunch {
+  int64_t grid;
+  int grouped;
+};
+static RopeLaunch rope_launch(int64_t tokens, int64_t H, int blocks_per_sm, int vec_per_block) {
+  static const bool strided = getenv("VBX_QKROPE_ORDER") != nullptr && getenv("VBX_QKROPE_ORDER")[0] == 's';
+  RopeLaunch r;
+  r.grouped = (!strided && vec_per_block % (2 * H) == 0) ? 1 : 0;
+  if (r.grouped) {
+    const int64_t step = vec_per_block / (2 * H), group = step > kTokGroup ? step : kTokGroup;
+    const int64_t groups = (tokens + group - 1) / group, cap = (int64_t)kNumSM * blocks_per_sm;
+    r.grid = groups < cap ? groups : cap;
+  } else {
+    r.grid = rope_grid(tokens * 2 * H, H, blocks_per_sm, vec_per_block);
+  }
+  return r;
 }
 
 extern "C" int vbx_qkrope_fwd(const uint16_t* qkv, const float* cosv, const float* sinv, const float* gq, const float* gk,
@@ -206,7 +354,13 @@ extern "C" int vbx_qkrope_fwd(const uint16_t* qkv, const float* cosv, const floa
   VBX_REQUIRE(B > 0 && N > 0 && H > 0, VBX_E_SHAPE);
   VBX_REQUIRE(VBX_ALIGNED16(qkv) && VBX_ALIGNED16(qh) && VBX_ALIGNED16(kh), VBX_E_ALIGN);
   const int64_t nvec = B * N * 2 * H;
-  qkrope_fwd_kernel<<<(unsigned)rope_grid(nvec, H, 8), 256, 0, (cudaStream_t)stream>>>(qkv, cosv, sinv, gq, gk, qh, kh, B, N, (int)H);
+  const RopeLaunch rl = rope_launch(B * N, H, VBX_QKROPE_FWD_MINB, kVecPerBlock);
+  const int64_t step = kVecPerBlock / (2 * H);
+  const bool un = rl.grouped && step >= 1 && ((step > kTokGroup ? 1 : kTokGroup / step) % VBX_QKROPE_FWD_U == 0);
+  if (un)
+    qkrope_fwd_kernel<VBX_QKROPE_FWD_U><<<(unsigned)rl.grid, 256, 0, (cudaStream_t)stream>>>(qkv, cosv, sinv, gq, gk, qh, kh, B, N, (int)H, rl.grouped);
+  else
+    qkrope_fwd_kernel<1><<<(unsigned)rl.grid, 256, 0, (cudaStream_t)stream>>>(qkv, cosv, sinv, gq, gk, qh, kh, B, N, (int)H, rl.grouped);
   return VBX_LAUNCH_RC();
 }
 
@@ -219,8 +373,15 @@ extern "C" int vbx_qkrope_bwd(const uint16_t* qkv, const float* cosv, const floa
   VBX_REQUIRE(B > 0 && N > 0 && H > 0, VBX_E_SHAPE);
   VBX_REQUIRE(VBX_ALIGNED16(qkv) && VBX_ALIGNED16(dqh) && VBX_ALIGNED16(dkh) && VBX_ALIGNED16(dqkv), VBX_E_ALIGN);
   const int64_t nvec = B * N * 2 * H;
-  // 2 resident blocks per SM (122 registers; forcing 3 spills and is slower): more blocks would only multiply the dgamma atomics
-  qkrope_bwd_kernel<<<(unsigned)rope_grid(nvec, H, 2), 256, 0, (cudaStream_t)stream>>>(qkv, cosv, sinv, gq, gk, dqh, dkh, dqkv, dgq, dgk, B, N,
-                                                                      (int)H);
+  const RopeLaunch rl = rope_launch(B * N, H, VBX_QKROPE_BWD_MINB, kVecPerBlockB);
+  // VBX_QKROPE_BWD_U (4) vectors in flight per thread when the grouped walk has a multiple of that many passes per group, else one
+  const int64_t step = kVecPerBlockB / (2 * H > 0 ? 2 * H : 1);
+  const bool u4 = rl.grouped && step >= 1 && ((step > kTokGroup ? 1 : kTokGroup / step) % VBX_QKROPE_BWD_U == 0);
+  if (u4)
+    qkrope_bwd_kernel<VBX_QKROPE_BWD_U><<<(unsigned)rl.grid, 256, 0, (cudaStream_t)stream>>>(qkv, cosv, sinv, gq, gk, dqh, dkh, dqkv, dgq, dgk, B, N, (int)H,
+                                                                              rl.grouped);
+  else
+    qkrope_bwd_kernel<1><<<(unsigned)rl.grid, 256, 0, (cudaStream_t)stream>>>(qkv, cosv, sinv, gq, gk, dqh, dkh, dqkv, dgq, dgk, B, N, (int)H,
+                                                                              rl.grouped);
   return VBX_LAUNCH_RC();
 }
