@@ -389,9 +389,10 @@ def main():
     ap.add_argument('--batch', type=int, default=64, help='batch per GPU (BASELINE configs[2]: 64)')
     ap.add_argument('--depth', type=int, default=DEPTH)
     ap.add_argument('--no-sample', action='store_true')
-    ap.add_argument('--optimizer', default=os.environ.get('VBX_OPTIMIZER', 'torch'), choices=['torch', 'flat'],
-                    help="'torch': torch.optim.Adam(fused=True) with the clip folded into its grad_scale; 'flat': "
-                         "voicebox_pytorch_b200.FlatAdam = one vbx_adam_step launch over the flat buffers (experiment)")
+    ap.add_argument('--optimizer', default=os.environ.get('VBX_OPTIMIZER', 'flat'), choices=['torch', 'flat'],
+                    help="'flat' (default; validated against torch Adam in tests/test_gpu_kernels.py): voicebox_pytorch_b200.FlatAdam = "
+                         "clip + Adam in one vbx_adam_step launch over the flat buffers; 'torch': torch.optim.Adam(fused=True) with the "
+                         "clip folded into its grad_scale")
     ap.add_argument('--allreduce', default=os.environ.get('VBX_ALLREDUCE', 'after'), choices=['overlap', 'after'],
                     help='gradient exchange: ONE all-reduce of the flat bucket after backward (default; measured faster: NCCL CTAs '
                          'otherwise take SMs from the 1-CTA/SM backward kernels), or chunked all-reduce overlapped with backward')
@@ -536,7 +537,8 @@ def main():
 
     # ---- device-resident timed region (value) --------------------------------------------------------------------------------
     tracked = ['vbx_attn_fwd', 'vbx_attn_bwd', 'vbx_adarms_fwd', 'vbx_adarms_bwd', 'vbx_geglu_fwd', 'vbx_geglu_bwd',
-               'vbx_qkrope_fwd', 'vbx_qkrope_bwd', 'vbx_convpos_fwd', 'vbx_convpos_bwd', 'vbx_ff1_geglu', 'vbx_pack_bf16',
+               'vbx_qkrope_fwd', 'vbx_qkrope_bwd', 'vbx_convpos_fwd', 'vbx_convpos_bwd', 'vbx_ff1_geglu', 'vbx_ff2_dgrad_geglu_bwd',
+               'vbx_pack_bf16',
                'vbx_accum_bf16_2d', 'vbx_accum_bf16_table', 'vbx_adam_step']
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = vbx._lib.launch_count
@@ -586,7 +588,7 @@ def main():
         'vbx_geglu_fwd': ('hbm', T * 2752 * 6.0), 'vbx_geglu_bwd': ('hbm', T * 2752 * 10.0),
         'vbx_qkrope_fwd': ('hbm', T * 2048 * 4.0), 'vbx_qkrope_bwd': ('hbm', T * 1024 * (2 + 2 + 2 + 4 + 2 + 2.0)),
         'vbx_convpos_fwd': ('hbm', B * N * D * 6.0), 'vbx_convpos_bwd': ('hbm', B * N * D * 10.0),
-        'vbx_ff1_geglu': ('tensor', 2.0 * T * D * 2 * 2752),
+        'vbx_ff1_geglu': ('tensor', 2.0 * T * D * 2 * 2752), 'vbx_ff2_dgrad_geglu_bwd': ('tensor', 2.0 * T * D * 2752),
         'vbx_pack_bf16': ('hbm', n_params * 6.0), 'vbx_adam_step': ('hbm', n_params * 28.0),
     }
     kernels = {}
@@ -602,7 +604,7 @@ def main():
         peak = peaks['tf_sustained'] if kind == 'tensor' else peaks['hbm']
         kernels[name] = dict(bound=kind, launches_per_step=cnt / args.steps, avg_us=avg_ms * 1e3, ms_per_step=tot_ms / args.steps,
                              achieved=ach, peak=peak, unit='TFLOP/s' if kind == 'tensor' else 'GB/s', frac=ach / peak)
-    own = [k for k in kernels if 'frac' in kernels[k] and k != 'vbx_ff1_geglu']
+    own = [k for k in kernels if 'frac' in kernels[k] and k not in ('vbx_ff1_geglu', 'vbx_ff2_dgrad_geglu_bwd')]
     dom = max(own, key=lambda k: kernels[k]['ms_per_step']) if own else None
     traffic = None
     try:

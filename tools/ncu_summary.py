@@ -70,7 +70,7 @@ def main():
                 ir, iw = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
                 tot = float(d[ir].replace(',', '')) * SCALE.get(units[ir], 1.0) + float(d[iw].replace(',', '')) * SCALE.get(units[iw], 1.0)
                 for key, entry in ENTRY.items():
-                    if k.startswith(key) or key in k:
+                    if k.startswith(key):
                         traffic.setdefault(entry, []).append(tot)
                         break
         lines.append('')
