@@ -226,6 +226,9 @@ def _attn_reference(qkv, H, gq, gk, pos, inv_freq, scale, key_mask):
     (2, 2, 300, 0, False, True),       # multi-tile, no qk-norm (smooth softmax: tight check of the dQ/dK/dV GEMMs)
     (1, 16, 1040, 16, True, False),    # cfg3 geometry: 8 full tiles + 16
     (2, 3, 100, 0, True, False),       # 2H = 6 does not divide a block's vector slots: the strided token order of the rope kernels
+    (1, 1, 70, 0, True, False),        # one head: a rope block covers 16 / 32 tokens per pass (group > 8 tokens, single pass)
+    (2, 8, 150, 16, True, False),      # 2H = 16: two / four tokens per pass
+    (1, 32, 100, 0, True, False),      # 2H = 64: grouped forward, strided backward
 ])
 def test_attention_fwd_bwd(vbx, B, H, N, R, qk_norm, masked):
     """qk-norm + rotary prologue + tcgen05 flash attention vs the fp32 oracle (vp.py:320-332, attend.py:119-137).
