@@ -117,6 +117,29 @@ constexpr uint32_t kColO = 128, kColP = 192;
 constexpr int kThreads = 320;
 }  // namespace fwd
 
+// packed-fp32 helpers of the forward softmax (VBX_FWD_F32X2=0 restores the scalar instruction streams for A/B runs)
+#ifndef VBX_FWD_F32X2
+#define VBX_FWD_F32X2 1
+#endif
+VBX_DEVINL float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+VBX_DEVINL void fma_scale32(float (&acc)[32], float alpha, const float (&v)[32]) {   // acc = acc * alpha + v
+#if VBX_FWD_F32X2
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    const float2 t = __ffma2_rn(make_float2(acc[i], acc[i + 1]), make_float2(alpha, alpha), make_float2(v[i], v[i + 1]));
+    acc[i] = t.x;
+    acc[i + 1] = t.y;
+  }
+#else
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = fmaf(acc[i], alpha, v[i]);
+#endif
+}
+
 __global__ void __launch_bounds__(fwd::kThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
                 const __grid_constant__ CUtensorMap mv, const uint8_t* __restrict__ key_mask, float scale_log2,
@@ -280,8 +303,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
           for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaf(s[i], scale_log2, bias[c * 32 + i]));
         } else {
           float m4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+#if VBX_FWD_F32X2
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {   // sm_100 3-input max: half the instructions of the max chain
+            m4[0] = fmax3(m4[0], s[i], s[i + 1]);
+            m4[1] = fmax3(m4[1], s[i + 2], s[i + 3]);
+            m4[2] = fmax3(m4[2], s[i + 4], s[i + 5]);
+            m4[3] = fmax3(m4[3], s[i + 6], s[i + 7]);
+          }
+#else
 #pragma unroll
           for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], s[i]);
+#endif
           mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale_log2);  // scale > 0
         }
       }
@@ -299,8 +332,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         tc_fence_after();
         float v[32];
         tmem_ld32(t_lane + kColO + half * 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = fmaf(acc[i], alpha_prev, v[i]);
+        fma_scale32(acc, alpha_prev, v);
         tc_fence_before();
       }
       alpha_prev = alpha;
@@ -336,13 +368,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
             s[i] = ex2(t + neg_m);
           }
         } else {
+#if VBX_FWD_F32X2
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {   // every key exists: no -inf here.  Packed fp32 FMA: same rounding, half the issue slots
+            const float2 t = __ffma2_rn(make_float2(s[i], s[i + 1]), make_float2(scale_log2, scale_log2), make_float2(neg_m, neg_m));
+            s[i] = VBX_EX2_AT(i, t.x);
+            s[i + 1] = VBX_EX2_AT(i + 1, t.y);
+          }
+#else
 #pragma unroll
           for (int i = 0; i < 32; ++i) s[i] = VBX_EX2_AT(i, fmaf(s[i], scale_log2, neg_m));  // every key exists: no -inf here
+#endif
         }
+#if VBX_FWD_F32X2
+        float2 r2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {     // same four partial sums (i & 3) as the scalar chain, two per packed add
+          r2[0] = __fadd2_rn(r2[0], make_float2(s[i], s[i + 1]));
+          r2[1] = __fadd2_rn(r2[1], make_float2(s[i + 2], s[i + 3]));
+        }
+        rowsum += (r2[0].x + r2[0].y) + (r2[1].x + r2[1].y);
+#else
         float r4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < 32; ++i) r4[i & 3] += s[i];
         rowsum += (r4[0] + r4[1]) + (r4[2] + r4[3]);
+#endif
         uint32_t pk[16];
 #pragma unroll
         for (int x = 0; x < 16; ++x) {
@@ -363,8 +414,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
       tc_fence_after();
       float v[32];
       tmem_ld32(t_lane + kColO + half * 32, v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) acc[i] = fmaf(acc[i], alpha_prev, v[i]);
+      fma_scale32(acc, alpha_prev, v);
       tc_fence_before();
     }
     // epilogue: total row sum (both halves), normalise, merge heads ('b h n d -> b n (h d)'), log-sum-exp for the backward
@@ -1464,10 +1514,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         for (int x = 0; x < 16; x += 2) {
           // padded queries (-lse = -inf) may come out as 2^-125 instead of 0 from the polynomial: they only ever multiply
           // zero-filled dO / Q rows and clipped dQ rows
+#if VBX_FWD_F32X2
+          // packed fp32 (FFMA2 / FADD2 / FMUL2): same roundings as the scalar lines below, three issue slots per pair fewer
+          const float2 lr = *reinterpret_cast<const float2*>(lrow + x), dr = *reinterpret_cast<const float2*>(drow + x);
+          const float2 a2 = __ffma2_rn(make_float2(s[x], s[x + 1]), make_float2(scale_log2, scale_log2), lr);
+          const float p0 = VBX_EX2_AT(x, a2.x);
+          const float p1 = VBX_EX2_AT(x + 1, a2.y);
+          const float2 d2 = __fmul2_rn(make_float2(p0, p1), __fadd2_rn(make_float2(dp[x], dp[x + 1]), make_float2(-dr.x, -dr.y)));
+          const float d0 = d2.x, d1 = d2.y;
+#else
           const float p0 = VBX_EX2_AT(x, fmaf(s[x], scale_log2, lrow[x]));
           const float p1 = VBX_EX2_AT(x + 1, fmaf(s[x + 1], scale_log2, lrow[x + 1]));
           const float d0 = p0 * (dp[x] - drow[x]);
           const float d1 = p1 * (dp[x + 1] - drow[x + 1]);
+#endif
           __nv_bfloat162 pp = f2bf(p0, p1), dd = f2bf(d0, d1);
           pk[c * 8 + (x >> 1)] = *reinterpret_cast<uint32_t*>(&pp);
           dsk[c * 8 + (x >> 1)] = *reinterpret_cast<uint32_t*>(&dd);
