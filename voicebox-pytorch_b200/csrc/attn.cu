@@ -1510,28 +1510,40 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         }
         const float* lrow = lrow_w + c * 16;       // -lse
         const float* drow = lrow_w + 32 + c * 16;  // delta
+#if VBX_FWD_F32X2
+        // packed fp32 (FFMA2 / FADD2 / FMUL2): same roundings as the scalar lines, three issue slots per pair fewer.  The 32 -lse /
+        // delta values of this warp's query columns are the same for every lane: 16-byte broadcast loads (one shared-memory
+        // wavefront per four columns; the 8-byte version cost 512 wavefronts per tile of a kernel bound by shared-memory bandwidth)
+#pragma unroll
+        for (int x = 0; x < 16; x += 4) {
+          const float4 lr = *reinterpret_cast<const float4*>(lrow + x), dr = *reinterpret_cast<const float4*>(drow + x);
+          const float2 a01 = __ffma2_rn(make_float2(s[x], s[x + 1]), make_float2(scale_log2, scale_log2), make_float2(lr.x, lr.y));
+          const float2 a23 = __ffma2_rn(make_float2(s[x + 2], s[x + 3]), make_float2(scale_log2, scale_log2), make_float2(lr.z, lr.w));
+          // padded queries (-lse = -inf) may come out as 2^-125 instead of 0 from the polynomial: they only ever multiply
+          // zero-filled dO / Q rows and clipped dQ rows
+          const float p0 = VBX_EX2_AT(x, a01.x), p1 = VBX_EX2_AT(x + 1, a01.y), p2 = VBX_EX2_AT(x + 2, a23.x), p3 = VBX_EX2_AT(x + 3, a23.y);
+          const float2 d01 = __fmul2_rn(make_float2(p0, p1), __fadd2_rn(make_float2(dp[x], dp[x + 1]), make_float2(-dr.x, -dr.y)));
+          const float2 d23 = __fmul2_rn(make_float2(p2, p3), __fadd2_rn(make_float2(dp[x + 2], dp[x + 3]), make_float2(-dr.z, -dr.w)));
+          __nv_bfloat162 pa = f2bf(p0, p1), pb = f2bf(p2, p3), da = f2bf(d01.x, d01.y), db = f2bf(d23.x, d23.y);
+          pk[c * 8 + (x >> 1)] = *reinterpret_cast<uint32_t*>(&pa);
+          pk[c * 8 + (x >> 1) + 1] = *reinterpret_cast<uint32_t*>(&pb);
+          dsk[c * 8 + (x >> 1)] = *reinterpret_cast<uint32_t*>(&da);
+          dsk[c * 8 + (x >> 1) + 1] = *reinterpret_cast<uint32_t*>(&db);
+        }
+#else
 #pragma unroll
         for (int x = 0; x < 16; x += 2) {
           // padded queries (-lse = -inf) may come out as 2^-125 instead of 0 from the polynomial: they only ever multiply
           // zero-filled dO / Q rows and clipped dQ rows
-#if VBX_FWD_F32X2
-          // packed fp32 (FFMA2 / FADD2 / FMUL2): same roundings as the scalar lines below, three issue slots per pair fewer
-          const float2 lr = *reinterpret_cast<const float2*>(lrow + x), dr = *reinterpret_cast<const float2*>(drow + x);
-          const float2 a2 = __ffma2_rn(make_float2(s[x], s[x + 1]), make_float2(scale_log2, scale_log2), lr);
-          const float p0 = VBX_EX2_AT(x, a2.x);
-          const float p1 = VBX_EX2_AT(x + 1, a2.y);
-          const float2 d2 = __fmul2_rn(make_float2(p0, p1), __fadd2_rn(make_float2(dp[x], dp[x + 1]), make_float2(-dr.x, -dr.y)));
-          const float d0 = d2.x, d1 = d2.y;
-#else
           const float p0 = VBX_EX2_AT(x, fmaf(s[x], scale_log2, lrow[x]));
           const float p1 = VBX_EX2_AT(x + 1, fmaf(s[x + 1], scale_log2, lrow[x + 1]));
           const float d0 = p0 * (dp[x] - drow[x]);
           const float d1 = p1 * (dp[x + 1] - drow[x + 1]);
-#endif
           __nv_bfloat162 pp = f2bf(p0, p1), dd = f2bf(d0, d1);
           pk[c * 8 + (x >> 1)] = *reinterpret_cast<uint32_t*>(&pp);
           dsk[c * 8 + (x >> 1)] = *reinterpret_cast<uint32_t*>(&dd);
         }
+#endif
       }
       if (dead_row) {  // rare (tail tile / masked keys): the whole row of P^T and dS^T is zero
 #pragma unroll
