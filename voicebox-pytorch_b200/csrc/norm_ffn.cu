@@ -13,6 +13,10 @@ VBX_DEVINL int grp(int c, int hf, int lane) { return c * 256 + hf * 128 + lane *
 // ------------------------------------------------------------------------------------------------------------------
 // residual add + (adaptive) RMSNorm, forward.   One warp per token row; element ownership: grp() above.
 // ------------------------------------------------------------------------------------------------------------------
+#ifndef VBX_ADARMS_FWD_ROWS
+#define VBX_ADARMS_FWD_ROWS 1
+#endif
+constexpr int kAdarmsFwdRows = VBX_ADARMS_FWD_ROWS;   // rows per warp (A/B knob: 1 = one row per warp, the round-1 shape)
 template <int C>
 __global__ void __launch_bounds__(256, (C <= 4) ? 4 : 2) adarms_fwd_kernel(const float* __restrict__ x_in, int64_t xbs, int64_t row0,
                                                           const uint16_t* __restrict__ branch,
@@ -21,20 +25,23 @@ __global__ void __launch_bounds__(256, (C <= 4) ? 4 : 2) adarms_fwd_kernel(const
                                                           float* __restrict__ rstd, int64_t B, int64_t rows, int D) {
   const int lane = threadIdx.x & 31;
   const float sqrt_d = sqrtf((float)D);
-  // one row per warp, one block per 8 rows: the hardware block scheduler balances the tail (a grid-stride loop with ~7
-  // rows per warp costs up to 1/7 in imbalance)
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // one block per 8 * kAdarmsFwdRows consecutive rows, a warp takes every 8th of them; the hardware block scheduler balances the
+  // tail (a grid-stride loop over all rows costs up to 1/7 in imbalance).  With more than one row per warp, lane 0 announces the
+  // warp's NEXT row to L2 before it starts on the current one.
+  const int nwarp = blockDim.x >> 5;
+#pragma unroll 1
+  for (int rr = 0; rr < kAdarmsFwdRows; ++rr) {
+  const int64_t row = ((int64_t)blockIdx.x * kAdarmsFwdRows + rr) * nwarp + (threadIdx.x >> 5);
   if (row < B * rows) {
     const int64_t b = row / rows, r = row - b * rows;
     const float* xi = x_in + b * xbs + (row0 + r) * D;
     float v[C][8];
     float ss = 0.f;
     const uint16_t* bri = branch != nullptr ? branch + b * xbs + (row0 + r) * D : nullptr;
-    {
-      // the block that will take this SM slot next is ~one residency wave (4 blocks x 148 SMs x 8 rows) ahead: announce its row
-      const int64_t ahead = row + (int64_t)kNumSM * 4 * 8;
-      if (lane == 0 && ahead < B * rows && (D & 7) == 0) {
-        const int64_t b2 = ahead / rows, r2 = ahead - b2 * rows;
+    if (kAdarmsFwdRows > 1 && rr + 1 < kAdarmsFwdRows) {
+      const int64_t nxt = row + nwarp;
+      if (lane == 0 && nxt < B * rows && (D & 7) == 0) {
+        const int64_t b2 = nxt / rows, r2 = nxt - b2 * rows;
         prefetch_l2_bulk(x_in + b2 * xbs + (row0 + r2) * D, (uint32_t)D * 4u);
         if (branch != nullptr) prefetch_l2_bulk(branch + b2 * xbs + (row0 + r2) * D, (uint32_t)D * 2u);
       }
@@ -95,6 +102,7 @@ __global__ void __launch_bounds__(256, (C <= 4) ? 4 : 2) adarms_fwd_kernel(const
         }
       }
     }
+  }
   }
 }
 
@@ -319,7 +327,7 @@ extern "C" int vbx_adarms_fwd(const float* x_in, int64_t x_batch_stride, int64_t
                   (!beta || VBX_ALIGNED16(beta)) && (!x_out || VBX_ALIGNED16(x_out)),
               VBX_E_ALIGN);
   if (x_out != nullptr && x_out == x_in) VBX_REQUIRE(x_batch_stride == rows * D && row0 == 0, VBX_E_SHAPE);
-  const int64_t nblk = (B * rows + 7) / 8;
+  const int64_t nblk = (B * rows + 8 * kAdarmsFwdRows - 1) / (8 * kAdarmsFwdRows);
   VBX_REQUIRE(nblk < (1ll << 31), VBX_E_SHAPE);
   const int grid = (int)nblk;
   cudaStream_t s = (cudaStream_t)stream;
