@@ -229,6 +229,7 @@ def _attn_reference(qkv, H, gq, gk, pos, inv_freq, scale, key_mask):
     (1, 1, 70, 0, True, False),        # one head: a rope block covers 16 / 32 tokens per pass (group > 8 tokens, single pass)
     (2, 8, 150, 16, True, False),      # 2H = 16: two / four tokens per pass
     (1, 32, 100, 0, True, False),      # 2H = 64: grouped forward, strided backward
+    (3, 16, 131, 0, True, False),      # H = 16: the staged rope backward; 393 tokens = 98 stages of four + a one-token tail
 ])
 def test_attention_fwd_bwd(vbx, B, H, N, R, qk_norm, masked):
     """qk-norm + rotary prologue + tcgen05 flash attention vs the fp32 oracle (vp.py:320-332, attend.py:119-137).

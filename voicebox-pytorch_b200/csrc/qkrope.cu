@@ -2,7 +2,7 @@
 // rotary embedding (vp.py:193-199) and the 'b n (h d) -> b h n d' head split (vp.py:321), in ONE pass over the q and k
 // blocks of the to_qkv GEMM output.  cos/sin come from a torch-computed table so the
 // -10000 register-token position (vp.py:440) gets a correctly range-reduced angle.
-#include "common.cuh"
+#include "umma.cuh"
 
 namespace vbx {
 
@@ -314,6 +314,172 @@ __global__ void __launch_bounds__(256, VBX_QKROPE_BWD_MINB) qkrope_bwd_kernel(co
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// backward, staged variant for H = 16 (2H = 32 = the block's vector slots): the loads go through shared memory as 1-D bulk
+// copies (cp.async.bulk + mbarrier), so the bytes in flight are set by the stage size (40 KB per block, two blocks per SM) and
+// not by registers.  Stage = 4 consecutive tokens: per token one 4 KB copy of its q|k block of qkv, per (token, head) one 256 B
+// copy of dq (fp32) and one 128 B copy of dk (bf16) -- 132 copies, one per thread, all completing on one mbarrier.  While the
+// 256 threads work on stage i (same math, same thread <-> (which, head, slice) assignment as the register kernel above), stage
+// i+1 is in flight.  Results leave through registers as before.
+// ------------------------------------------------------------------------------------------------------------------
+namespace ropes {
+constexpr int kTok = 4, kH = 16, kStages = 2;
+constexpr uint32_t kXBytes = kTok * 2 * kH * kDh * 2;      // 16 KB: [tok][q|k][h][64] bf16
+constexpr uint32_t kDqBytes = kTok * kH * kDh * 4;          // 16 KB: [tok][h][64] f32
+constexpr uint32_t kDkBytes = kTok * kH * kDh * 2;          //  8 KB: [tok][h][64] bf16
+constexpr uint32_t kStageBytes = kXBytes + kDqBytes + kDkBytes;
+constexpr uint32_t kOffBar = kStages * kStageBytes;
+constexpr uint32_t kSmemBytes = kOffBar + 64;
+}  // namespace ropes
+
+VBX_DEVINL void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ptx::smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(ptx::smem_u32(bar))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2) qkrope_bwd_staged_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ cosv,
+                                                                    const float* __restrict__ sinv, const float* __restrict__ gq,
+                                                                    const float* __restrict__ gk, const float* __restrict__ dqh,
+                                                                    const uint16_t* __restrict__ dkh, uint16_t* __restrict__ dqkv,
+                                                                    float* __restrict__ dgq, float* __restrict__ dgk, int64_t B,
+                                                                    int64_t N) {
+  using namespace ropes;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  const int tid = threadIdx.x, sub = tid & 7, pair = tid >> 3, which = pair >> 4, h = pair & 15;
+  const int64_t total = B * N, groups = (total + kTok - 1) / kTok;
+  constexpr int H = kH;
+  if (tid == 0) {
+    ptx::mbar_init(&bars[0], 1);
+    ptx::mbar_init(&bars[1], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  const float* gam = which ? gk : gq;
+  float glo[4], ghi[4], dglo[4], dghi[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) glo[i] = ghi[i] = 1.f, dglo[i] = dghi[i] = 0.f;
+  if (gam != nullptr) {
+    ld4c(gam + h * kDh + sub * 4, glo);
+    ld4c(gam + h * kDh + 32 + sub * 4, ghi);
+  }
+  // one copy per thread: threads 0..3 the qkv token blocks, threads 4..131 the (token, which, head) gradient pieces
+  auto issue = [&](int64_t g, int stage) {
+    uint8_t* st = smem + stage * kStageBytes;
+    const int64_t tok0 = g * kTok;
+    if (tid == 0) {
+      const int64_t left = total - tok0;
+      const uint32_t ntok = left < kTok ? (uint32_t)left : (uint32_t)kTok;
+      ptx::mbar_arrive_expect_tx(&bars[stage], ntok * (kStageBytes / kTok));
+    }
+    if (tid < kTok) {
+      const int64_t tok = tok0 + tid;
+      if (tok < total) bulk_load_1d(st + tid * (kXBytes / kTok), qkv + tok * (3 * H * kDh), kXBytes / kTok, &bars[stage]);
+    } else if (tid < kTok + kTok * 2 * H) {
+      const int j = tid - kTok, t = j >> 5, p = j & 31, wh = p >> 4, hh = p & 15;
+      const int64_t tok = tok0 + t;
+      if (tok < total) {
+        const int64_t b = tok / N, n = tok - b * N;
+        const int64_t hoff = ((b * H + hh) * N + n) * kDh;
+        if (wh == 0) bulk_load_1d(st + kXBytes + (t * H + hh) * 256, dqh + hoff, 256, &bars[stage]);
+        else bulk_load_1d(st + kXBytes + kDqBytes + (t * H + hh) * 128, dkh + hoff, 128, &bars[stage]);
+      }
+    }
+  };
+  int it = 0;
+  if ((int64_t)blockIdx.x < groups) issue(blockIdx.x, 0);
+  for (int64_t g = blockIdx.x; g < groups; g += gridDim.x, ++it) {
+    const int stage = it & 1;
+    if (g + gridDim.x < groups) issue(g + gridDim.x, stage ^ 1);   // that buffer was released by the __syncthreads below
+    ptx::mbar_wait(&bars[stage], (it >> 1) & 1);
+    const uint8_t* st = smem + stage * kStageBytes;
+    int64_t tok = g * kTok;
+    int64_t b = tok / N, n = tok - b * N;
+#pragma unroll
+    for (int t = 0; t < kTok; ++t) {
+      const bool act = tok < total;
+      float dlo[4], dhi[4], xlo[4], xhi[4], cs[4], sn[4];
+      if (act) {
+        const uint8_t* xp = st + t * (kXBytes / kTok) + which * (H * kDh * 2) + h * (kDh * 2) + sub * 8;
+        const uint2 x0 = *reinterpret_cast<const uint2*>(xp), x1 = *reinterpret_cast<const uint2*>(xp + 64);
+        const float2 a = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&x0.x)), c = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&x0.y));
+        const float2 e = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&x1.x)), f = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&x1.y));
+        xlo[0] = a.x; xlo[1] = a.y; xlo[2] = c.x; xlo[3] = c.y;
+        xhi[0] = e.x; xhi[1] = e.y; xhi[2] = f.x; xhi[3] = f.y;
+        if (which) {
+          const uint8_t* dp = st + kXBytes + kDqBytes + (t * H + h) * 128 + sub * 8;
+          const uint2 d0 = *reinterpret_cast<const uint2*>(dp), d1 = *reinterpret_cast<const uint2*>(dp + 64);
+          const float2 a2 = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&d0.x)), c2 = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&d0.y));
+          const float2 e2 = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&d1.x)), f2 = bf2f(*reinterpret_cast<const __nv_bfloat162*>(&d1.y));
+          dlo[0] = a2.x; dlo[1] = a2.y; dlo[2] = c2.x; dlo[3] = c2.y;
+          dhi[0] = e2.x; dhi[1] = e2.y; dhi[2] = f2.x; dhi[3] = f2.y;
+        } else {
+          const uint8_t* dp = st + kXBytes + (t * H + h) * 256 + sub * 16;
+          const float4 d0 = *reinterpret_cast<const float4*>(dp), d1 = *reinterpret_cast<const float4*>(dp + 128);
+          dlo[0] = d0.x; dlo[1] = d0.y; dlo[2] = d0.z; dlo[3] = d0.w;
+          dhi[0] = d1.x; dhi[1] = d1.y; dhi[2] = d1.z; dhi[3] = d1.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dlo[i] = dhi[i] = 0.f, xlo[i] = xhi[i] = 1.f;   // keeps the lanes in the shuffles, results unused
+      }
+      const int nn = act ? (int)n : 0;
+      ld4c(cosv + nn * 32 + sub * 4, cs);
+      ld4c(sinv + nn * 32 + sub * 4, sn);
+      // undo the rotation (transpose): dz_lo = dy_lo c + dy_hi s ; dz_hi = dy_hi c - dy_lo s
+      float zlo[4], zhi[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        zlo[i] = fmaf(dlo[i], cs[i], dhi[i] * sn[i]);
+        zhi[i] = fmaf(dhi[i], cs[i], -dlo[i] * sn[i]);
+      }
+      if (gam != nullptr) {
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ss = fmaf(xlo[i], xlo[i], fmaf(xhi[i], xhi[i], ss));
+        ss = sum8(ss);
+        const float rinv = fminf(rsqrtf(ss), 1e12f);
+        const float s1 = 8.0f * rinv;
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (act) {
+            dglo[i] = fmaf(zlo[i] * xlo[i], s1, dglo[i]);  // dgamma += dz * xhat * 8
+            dghi[i] = fmaf(zhi[i] * xhi[i], s1, dghi[i]);
+          }
+          zlo[i] *= glo[i];
+          zhi[i] *= ghi[i];
+          dot = fmaf(zlo[i], xlo[i], fmaf(zhi[i], xhi[i], dot));
+        }
+        dot = sum8(dot);
+        const float s2 = s1 * rinv * rinv * dot;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          zlo[i] = fmaf(zlo[i], s1, -xlo[i] * s2);
+          zhi[i] = fmaf(zhi[i], s1, -xhi[i] * s2);
+        }
+      }
+      if (act) {
+        uint16_t* dst = dqkv + tok * (3 * H * kDh) + which * (H * kDh) + h * kDh + sub * 4;
+        st4h(dst, zlo);
+        st4h(dst + 32, zhi);
+      }
+      ++tok;
+      if (++n >= N) { n = 0; ++b; }
+    }
+    __syncthreads();   // every thread has read this stage: the next issue() may overwrite it
+  }
+  if (gam != nullptr) {
+    float* dg = (which ? dgk : dgq) + h * kDh + sub * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      atomicAdd(dg + i, dglo[i]);
+      atomicAdd(dg + 32 + i, dghi[i]);
+    }
+  }
+}
+
 }  // namespace vbx
 
 using namespace vbx;
@@ -373,6 +539,17 @@ extern "C" int vbx_qkrope_bwd(const uint16_t* qkv, const float* cosv, const floa
   VBX_REQUIRE(B > 0 && N > 0 && H > 0, VBX_E_SHAPE);
   VBX_REQUIRE(VBX_ALIGNED16(qkv) && VBX_ALIGNED16(dqh) && VBX_ALIGNED16(dkh) && VBX_ALIGNED16(dqkv), VBX_E_ALIGN);
   const int64_t nvec = B * N * 2 * H;
+  // H = 16: the shared-memory staged kernel (VBX_QKROPE_BWD=regs selects the register kernel for A/B runs)
+  static const bool regs_only = getenv("VBX_QKROPE_BWD") != nullptr && getenv("VBX_QKROPE_BWD")[0] == 'r';
+  if (H == ropes::kH && !regs_only && VBX_ALIGNED16(qkv) && (N * 64 * 2) % 16 == 0) {
+    const int64_t groups = (B * N + ropes::kTok - 1) / ropes::kTok;
+    const int64_t grid = groups < 2 * kNumSM ? groups : 2 * kNumSM;
+    cudaError_t ce = cudaFuncSetAttribute(qkrope_bwd_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ropes::kSmemBytes);
+    if (ce != cudaSuccess) return (int)ce;
+    qkrope_bwd_staged_kernel<<<(unsigned)grid, 256, ropes::kSmemBytes, (cudaStream_t)stream>>>(qkv, cosv, sinv, gq, gk, dqh, dkh, dqkv, dgq,
+                                                                                               dgk, B, N);
+    return VBX_LAUNCH_RC();
+  }
   const RopeLaunch rl = rope_launch(B * N, H, VBX_QKROPE_BWD_MINB, kVecPerBlockB);
   // VBX_QKROPE_BWD_U (4) vectors in flight per thread when the grouped walk has a multiple of that many passes per group, else one
   const int64_t step = kVecPerBlockB / (2 * H > 0 ? 2 * H : 1);
