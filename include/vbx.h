@@ -179,11 +179,12 @@ int vbx_adam_step(float* p, const float* g, float* m, float* v, uint16_t* p_bf16
  *                                                                 apply_rotary_pos_emb) incl. vp.py:193-199, 280-287
  * qkv bf16 [B, N, 3*H*64] (q | k | v blocks, each h-major d-minor, vp.py:320-321);
  * cosv/sinv f32 [N,32] = cos/sin(pos (x) inv_freq) (half-split rotary: pairs (d, d+32));
- * gq/gk f32 [H,64] or NULL (no qk-norm).  Writes qh, kh bf16 [B,H,N,64]:
+ * gq/gk f32 [H,64] or NULL (no qk-norm).  Writes qh, kh bf16 [B,N,H,64] (token-major:
+ * the rope kernels move whole-token contiguous runs, the attention kernels address tiles through tensor-map strides):
  *   q^ = rot( q/max(||q||,1e-12) * 8 * gq )     (norm skipped when gq NULL) */
 int vbx_qkrope_fwd(const uint16_t* qkv, const float* cosv, const float* sinv, const float* gq, const float* gk,
                    uint16_t* qh, uint16_t* kh, int64_t B, int64_t N, int64_t H, void* stream);
-/* dqh f32 [B,H,N,64] (atomically accumulated by vbx_attn_bwd), dkh bf16 [B,H,N,64] -> writes the q and k blocks of
+/* dqh f32 [B,N,H,64] (accumulated by vbx_attn_bwd's TMA reduce-adds), dkh bf16 [B,N,H,64] -> writes the q and k blocks of
  * dqkv (bf16 [B,N,3*H*64]; the v block is written by vbx_attn_bwd) and accumulates dgq, dgk f32 [H,64]. */
 int vbx_qkrope_bwd(const uint16_t* qkv, const float* cosv, const float* sinv, const float* gq, const float* gk,
                    const float* dqh, const uint16_t* dkh, uint16_t* dqkv, float* dgq, float* dgk, int64_t B, int64_t N,
@@ -193,12 +194,12 @@ int vbx_qkrope_bwd(const uint16_t* qkv, const float* cosv, const float* sinv, co
  * Attention core (tcgen05 + TMEM + TMA)                           replaces attend.py:100-137 (math path) /
  *                                                                 attend.py:71-98 (SDPA path), head merge vp.py:332
  *   O = softmax(scale * Q K^T, masked keys -> -FLT_MAX) V          dim_head = 64
- * q,k bf16 [B,H,N,64]; v bf16 addressed v + b*v_bs + n*v_ns + h*64 (element strides; lets V be read in place from
+ * q,k bf16 [B,N,H,64] (as written by vbx_qkrope_fwd); v bf16 addressed v + b*v_bs + n*v_ns + h*64 (element strides; lets V be read in place from
  * the qkv GEMM output); key_mask uint8 [B,N] or NULL; o bf16 [B,N,H*64]; lse f32 [B,H,N] (log2 domain, for bwd). */
 int vbx_attn_fwd(const uint16_t* q, const uint16_t* k, const uint16_t* v, int64_t v_bs, int64_t v_ns,
                  const uint8_t* key_mask, float scale, uint16_t* o, float* lse, int64_t B, int64_t H, int64_t N,
                  void* stream);
-/* delta f32 [B,H,N] workspace; dq f32 [B,H,N,64] ACCUMULATED (caller zeroes); dk bf16 [B,H,N,64];
+/* delta f32 [B,H,N] workspace; dq f32 [B,N,H,64] ACCUMULATED (caller zeroes); dk bf16 [B,N,H,64];
  * dv bf16 addressed like v (dv_bs/dv_ns). */
 int vbx_attn_bwd(const uint16_t* q, const uint16_t* k, const uint16_t* v, int64_t v_bs, int64_t v_ns,
                  const uint8_t* key_mask, float scale, const uint16_t* o, const uint16_t* dout, const float* lse,

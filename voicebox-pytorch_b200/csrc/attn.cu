@@ -1585,7 +1585,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
     {
       const bool live = key < N;
       uint16_t* dvp = dv + (int64_t)b * dv_bs + (int64_t)(live ? key : 0) * dv_ns + h * kDh + qr * 16;
-      uint16_t* dkp = dk + (bh * N + (live ? key : 0)) * kDh + qr * 16;
+      uint16_t* dkp = dk + qk_vec_off(b, h, live ? key : 0, H, N) + qr * 16;
       float v[16];
       tmem_ld16(t_lane + kColDV + qr * 16, v);
       if (live) {
@@ -1755,6 +1755,12 @@ int make_tmap_bf16_4d(CUtensorMap* out, const void* base, int64_t N, int64_t H, 
 using namespace vbx;
 
 static const float kLog2e = 1.4426950408889634f;
+// (n, h, b) element strides of q^ / k^ / dq^ in the tensor maps (common.cuh: VBX_QK_TOKEN_MAJOR)
+#if VBX_QK_TOKEN_MAJOR
+#define VBX_QK_STRIDES(N, H) (H) * kDh, kDh, (N) * (H) * kDh
+#else
+#define VBX_QK_STRIDES(N, H) kDh, (N) * kDh, (H) * (N) * kDh
+#endif
 
 extern "C" int vbx_attn_fwd(const uint16_t* q, const uint16_t* k, const uint16_t* v, int64_t v_bs, int64_t v_ns,
                             const uint8_t* key_mask, float scale, uint16_t* o, float* lse, int64_t B, int64_t H, int64_t N,
@@ -1764,8 +1770,8 @@ extern "C" int vbx_attn_fwd(const uint16_t* q, const uint16_t* k, const uint16_t
   VBX_REQUIRE(VBX_ALIGNED16(o), VBX_E_ALIGN);
   CUtensorMap mq, mk, mv;
   int rc;
-  if ((rc = make_tmap_bf16_4d(&mq, q, N, H, B, kDh, N * kDh, H * N * kDh, kBM)) != VBX_OK) return rc;
-  if ((rc = make_tmap_bf16_4d(&mk, k, N, H, B, kDh, N * kDh, H * N * kDh, kBN)) != VBX_OK) return rc;
+  if ((rc = make_tmap_bf16_4d(&mq, q, N, H, B, VBX_QK_STRIDES(N, H), kBM)) != VBX_OK) return rc;
+  if ((rc = make_tmap_bf16_4d(&mk, k, N, H, B, VBX_QK_STRIDES(N, H), kBN)) != VBX_OK) return rc;
   if ((rc = make_tmap_bf16_4d(&mv, v, N, H, B, v_ns, kDh, v_bs, kBN)) != VBX_OK) return rc;
   // per call, not once per process: the attribute is per device, and a host process may drive several GPUs
   cudaError_t ce = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd::kSmemBytes);
@@ -1812,11 +1818,11 @@ extern "C" int vbx_attn_bwd(const uint16_t* q, const uint16_t* k, const uint16_t
               VBX_E_ALIGN);
   CUtensorMap mq, mk, mv, mdo, mdq;
   int rc;
-  if ((rc = make_tmap_bf16_4d(&mq, q, N, H, B, kDh, N * kDh, H * N * kDh, kBM)) != VBX_OK) return rc;
-  if ((rc = make_tmap_bf16_4d(&mk, k, N, H, B, kDh, N * kDh, H * N * kDh, kBN)) != VBX_OK) return rc;
+  if ((rc = make_tmap_bf16_4d(&mq, q, N, H, B, VBX_QK_STRIDES(N, H), kBM)) != VBX_OK) return rc;
+  if ((rc = make_tmap_bf16_4d(&mk, k, N, H, B, VBX_QK_STRIDES(N, H), kBN)) != VBX_OK) return rc;
   if ((rc = make_tmap_bf16_4d(&mv, v, N, H, B, v_ns, kDh, v_bs, kBN)) != VBX_OK) return rc;
   if ((rc = make_tmap_bf16_4d(&mdo, dout, N, H, B, H * kDh, kDh, N * H * kDh, kBM)) != VBX_OK) return rc;
-  if ((rc = make_tmap(&mdq, dq, kDh, N, H, B, kDh, N * kDh, H * N * kDh, 32, 4)) != VBX_OK) return rc;  // 32x32 fp32 boxes
+  if ((rc = make_tmap(&mdq, dq, kDh, N, H, B, VBX_QK_STRIDES(N, H), 32, 4)) != VBX_OK) return rc;  // 32x32 fp32 boxes
   cudaError_t ce = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd::kSmemBytes);
   if (ce != cudaSuccess) return (int)ce;  // per call: the attribute is per device
   cudaStream_t s = (cudaStream_t)stream;

@@ -143,6 +143,22 @@ VBX_DEVINL float ex2_approx(float x) {  // MUFU.EX2, rel err 2^-22; exp2f() adds
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Layout of the normed + rotated q / k and of their gradients between the rope kernels and the attention kernels.
+// 1 (shipped): token-major [B, N, H, 64] -- the rope kernels then read and write whole-token contiguous runs (2-4 KB) and the
+// attention kernels address tiles through their tensor maps' strides, exactly as they always did for V (read in place from the
+// qkv GEMM output) and dO.  0: head-major [B, H, N, 64] (rounds 1-2 until the last change; one 128-256 byte piece per (token, head)
+// on the rope side: 4.2-4.4 TB/s at best, profiles/r2_row_kernels_investigation.md).
+#ifndef VBX_QK_TOKEN_MAJOR
+#define VBX_QK_TOKEN_MAJOR 1
+#endif
+// element offset of head vector (b, h, n) in such a tensor
+VBX_DEVINL int64_t qk_vec_off(int64_t b, int64_t h, int64_t n, int64_t H, int64_t N) {
+#if VBX_QK_TOKEN_MAJOR
+  return ((b * N + n) * H + h) * 64;
+#else
+  return ((b * H + h) * N + n) * 64;
+#endif
+}
 // L2 prefetch of a contiguous, 16-byte aligned range (one instruction, no registers held): the row kernels are latency bound
 // at 14-32 resident warps per SM (ncu: every stall is long-scoreboard, DRAM at 3.3-4.7 TB/s), so each warp announces the NEXT
 // row it will touch while it works on the current one and its demand loads then hit L2.  VBX_ROW_PREFETCH=0 compiles it out.

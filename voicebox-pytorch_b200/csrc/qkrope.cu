@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256, VBX_QKROPE_FWD_MINB) qkrope_fwd_kernel(co
           ohi[i] = fmaf(hi[i], cs[i], lo[i] * sn[i]);
         }
         if (active) {
-          uint16_t* dst = (w.which ? kh : qh) + ((b_ * H + w.h) * N + n_) * kDh + sub * 8;
+          uint16_t* dst = (w.which ? kh : qh) + qk_vec_off(b_, w.h, n_, H, N) + sub * 8;
           stg_16(dst, pack8(olo));
           stg_16(dst + 32, pack8(ohi));
         }
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256, VBX_QKROPE_BWD_MINB) qkrope_bwd_kernel(co
         const bool act = tok < total;
         any |= act;
         const int64_t t_ = act ? tok : 0, b_ = act ? b : 0, n_ = act ? n : 0;
-        const int64_t hoff = ((b_ * H + w.h) * N + n_) * kDh + sub * 4;
+        const int64_t hoff = qk_vec_off(b_, w.h, n_, H, N) + sub * 4;
         const int64_t goff = t_ * (3 * H * kDh) + w.which * (H * kDh) + w.h * kDh + sub * 4;
         if (w.which) {
           const uint2 a = ldg_nc_8(dkh + hoff), c = ldg_nc_8(dkh + hoff + 32);
@@ -322,6 +322,9 @@ __global__ void __launch_bounds__(256, VBX_QKROPE_BWD_MINB) qkrope_bwd_kernel(co
 // 256 threads work on stage i (same math, same thread <-> (which, head, slice) assignment as the register kernel above), stage
 // i+1 is in flight.  Results leave through registers as before.
 // ------------------------------------------------------------------------------------------------------------------
+#ifndef VBX_ROPE_PIECE
+#define VBX_ROPE_PIECE 2048
+#endif
 namespace ropes {
 constexpr int kTok = 4, kH = 16, kStages = 2;
 constexpr uint32_t kXBytes = kTok * 2 * kH * kDh * 2;      // 16 KB: [tok][q|k][h][64] bf16
@@ -373,6 +376,21 @@ __global__ void __launch_bounds__(256, 2) qkrope_bwd_staged_kernel(const uint16_
       const uint32_t ntok = left < kTok ? (uint32_t)left : (uint32_t)kTok;
       ptx::mbar_arrive_expect_tx(&bars[stage], ntok * (kStageBytes / kTok));
     }
+#if VBX_QK_TOKEN_MAJOR
+    // a token's 10 KB = [4 KB q|k block of qkv | 4 KB dq (fp32) | 2 KB dk (bf16)], each contiguous in memory, fetched as
+    // kPiece-byte bulk copies (one per thread)
+    constexpr int kPiece = VBX_ROPE_PIECE, kPer = 10240 / kPiece;
+    static_assert(2048 % kPiece == 0 && kPiece % 16 == 0 && kTok * kPer <= 256, "pieces must tile the 4 KB / 4 KB / 2 KB runs exactly");
+    if (tid < kTok * kPer) {
+      const int t = tid / kPer, off = (tid - t * kPer) * kPiece;
+      const int64_t tok = tok0 + t;
+      if (tok < total) {
+        if (off < 4096) bulk_load_1d(st + t * 4096 + off, reinterpret_cast<const uint8_t*>(qkv + tok * (3 * H * kDh)) + off, kPiece, &bars[stage]);
+        else if (off < 8192) bulk_load_1d(st + kXBytes + t * 4096 + (off - 4096), reinterpret_cast<const uint8_t*>(dqh + tok * (H * kDh)) + (off - 4096), kPiece, &bars[stage]);
+        else bulk_load_1d(st + kXBytes + kDqBytes + t * 2048 + (off - 8192), reinterpret_cast<const uint8_t*>(dkh + tok * (H * kDh)) + (off - 8192), kPiece, &bars[stage]);
+      }
+    }
+#else
     if (tid < kTok) {
       const int64_t tok = tok0 + tid;
       if (tok < total) bulk_load_1d(st + tid * (kXBytes / kTok), qkv + tok * (3 * H * kDh), kXBytes / kTok, &bars[stage]);
@@ -386,6 +404,7 @@ __global__ void __launch_bounds__(256, 2) qkrope_bwd_staged_kernel(const uint16_
         else bulk_load_1d(st + kXBytes + kDqBytes + (t * H + hh) * 128, dkh + hoff, 128, &bars[stage]);
       }
     }
+#endif
   };
   int it = 0;
   if ((int64_t)blockIdx.x < groups) issue(blockIdx.x, 0);

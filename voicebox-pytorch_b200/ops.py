@@ -578,8 +578,8 @@ class _Attention(torch.autograd.Function):
         dev = qkv.device
         gq2 = None if gq is None else _c(gq.reshape(H, 64).float())
         gk2 = None if gk is None else _c(gk.reshape(H, 64).float())
-        qh = torch.empty((B, H, N, 64), device=dev, dtype=BF16)
-        kh = torch.empty((B, H, N, 64), device=dev, dtype=BF16)
+        qh = torch.empty((B, N, H, 64), device=dev, dtype=BF16)      # token-major (include/vbx.h)
+        kh = torch.empty((B, N, H, 64), device=dev, dtype=BF16)
         call('vbx_qkrope_fwd', ptr(qkv), ptr(cosv), ptr(sinv), ptr(gq2), ptr(gk2), ptr(qh), ptr(kh), B, N, H, stream())
         o = torch.empty((B, N, hd), device=dev, dtype=BF16)
         need_bwd = any(ctx.needs_input_grad)
@@ -598,8 +598,8 @@ class _Attention(torch.autograd.Function):
         B, N, H, hd, scale, gshape = ctx.geom
         dev = qkv.device
         do = _c(do)
-        dq = torch.zeros((B, H, N, 64), device=dev, dtype=torch.float32)
-        dk = torch.empty((B, H, N, 64), device=dev, dtype=BF16)
+        dq = torch.zeros((B, N, H, 64), device=dev, dtype=torch.float32)
+        dk = torch.empty((B, N, H, 64), device=dev, dtype=BF16)
         dqkv = torch.empty_like(qkv)
         delta = torch.empty((B, H, N), device=dev, dtype=torch.float32)
         v_ptr = qkv.data_ptr() + 2 * hd * 2
