@@ -1,6 +1,7 @@
-// Attention prologue / epilogue-of-backward: per-head RMSNorm of q and k (MultiheadRMSNorm, vp.py:280-287), half-split
-// rotary embedding (vp.py:193-199) and the 'b n (h d) -> b h n d' head split (vp.py:321), in ONE pass over the q and k
-// blocks of the to_qkv GEMM output.  cos/sin come from a torch-computed table so the
+// Attention prologue / epilogue-of-backward: per-head RMSNorm of q and k (MultiheadRMSNorm, vp.py:280-287) and half-split
+// rotary embedding (vp.py:193-199), in ONE pass over the q and k blocks of the to_qkv GEMM output.  The 'b n (h d) -> b h n d'
+// head split (vp.py:321) costs nothing: q^ / k^ stay token-major [B, N, H, 64] and the attention kernels pick a head's tile through
+// their tensor maps' strides (common.cuh: VBX_QK_TOKEN_MAJOR).  cos/sin come from a torch-computed table so the
 // -10000 register-token position (vp.py:440) gets a correctly range-reduced angle.
 #include "umma.cuh"
 
